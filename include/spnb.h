@@ -1,0 +1,135 @@
+/*
+ * spnb.h -- C ABI of libspnb.so, the B200 (sm_100a) particle-interaction library.
+ *
+ * This is the drop-in seam for SmoothParticleNets' native layer: it replaces the reference's
+ * `extern "C"` CUDA entry points in src/gpu_kernels.h:7-138 (and through them the pybind glue in
+ * src/cuda_layer_funcs.cpp and the vendored CUB 1.3.2).  Every function takes raw DEVICE pointers,
+ * plain sizes and a cudaStream_t passed as void*; there are no torch types here.
+ *
+ * Conventions shared by all entry points
+ *   - all tensors are contiguous float32, including index-valued ones (idxs, neighbors, cellStarts,
+ *     cellEnds, SDF idxs/offsets/shapes), exactly as in the reference;
+ *     `cellIDs` holds uint32 keys in a float-typed buffer like the reference GPU path
+ *     (gpu_kernels.cu:291);
+ *   - return value: 1 on success, 0 on failure (the reference's convention, gpu_kernels.cu:26-34);
+ *     on failure spnb_last_error() describes the problem;
+ *   - everything is stream-ordered: no host synchronisation, no device allocation, no global device
+ *     state is touched, so calls can be captured in CUDA graphs;
+ *   - outputs are OVERWRITTEN (the reference accumulates into caller-zeroed buffers); callers need
+ *     not pre-fill them;
+ *   - there is no CPU fallback.
+ */
+#ifndef SPNB_H_
+#define SPNB_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPNB_MAX_NDIM 19       /* ndim < MAX_CARTESIAN_DIM (src/constants.h:7) */
+#define SPNB_NUM_KERNEL_FNS 12 /* kernels.py:123: alphabetical ids 0..11 */
+
+/* Library version and the last error message of the calling thread ("" if none). */
+int spnb_version(void);
+const char* spnb_last_error(void);
+
+/* Replaces spn_max_cartesian_dim (cpu_layer_funcs.cpp:29-32). */
+int spnb_max_cartesian_dim(void);
+
+/* ---- hash-grid neighbour search ------------------------------------------------------------- */
+
+/* Bytes of device scratch needed by spnb_grid_bounds / spnb_hashgrid_order for these sizes.
+ * Replaces get_radixsort_buffer_size (gpu_kernels.h:113). */
+size_t spnb_hashgrid_workspace_bytes(int batch_size, int N, int ndims, int max_grid_dim);
+
+/* Per-scene grid bounds, bit-identical to the float32 torch ops of ParticleCollision.forward
+ * (ParticleCollision.py:174-181):
+ *   grid_dims = ceil(clamp((max-min)/radius, 0, max_grid_dim)),
+ *   low       = (min+max)/2 - grid_dims*radius/2.
+ * low, grid_dims: [batch_size, ndims]. */
+int spnb_grid_bounds(const float* locs, int batch_size, int N, int ndims, float radius,
+                     int max_grid_dim, float* low, float* grid_dims, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* Cell keys + STABLE sort of (key, original index) per scene.  Replaces cuda_hashgrid_order
+ * (gpu_kernels.h:63-74; kernel_compute_cellIDs + CUB SortPairs, gpu_kernels.cu:238-337).
+ *   cellIDs: [batch_size, N] sorted uint32 keys;  idxs: [batch_size, N] float, idxs[b,i] = original
+ *   index of the particle now at sorted position i (ties by ascending original index). */
+int spnb_hashgrid_order(const float* locs, const float* low, const float* grid_dims, float* cellIDs,
+                        float* idxs, void* workspace, size_t workspace_bytes, int batch_size, int N,
+                        int ndims, float cellEdge, int max_grid_dim, void* stream);
+
+/* Cell table + fixed-width neighbour lists.  Replaces cuda_compute_collisions
+ * (gpu_kernels.h:76-95; kernel_fill_cells + kernel_compute_collisions, gpu_kernels.cu:339-485).
+ *   cellStarts/cellEnds: [batch_size, ncells] float scratch tables (only the first
+ *   prod(grid_dims[b]) entries of each row are defined afterwards);
+ *   collisions: [batch_size, M, max_collisions] float: accepted particle indices in the reference's
+ *   visiting order, then -1 up to the end of the row.
+ *   trunc_flag (optional, may be NULL): device int that is atomically OR-ed with 1 if any row was cut
+ *   at max_collisions (consumers use it to choose the atomics-free symmetric backward). */
+int spnb_compute_collisions(const float* qlocs, const float* locs, const float* low,
+                            const float* grid_dims, const float* cellIDs, float* cellStarts,
+                            float* cellEnds, float* collisions, int batch_size, int M, int N,
+                            int ndims, int max_collisions, int ncells, float cellEdge, float radius,
+                            int include_self, int* trunc_flag, void* stream);
+
+/* Row permutation.  Replaces cuda_reorder_data (gpu_kernels.h:97-111).
+ *   reverse == 0: nlocs[b,i] = locs[b,idxs[b,i]];  reverse != 0: nlocs[b,idxs[b,i]] = locs[b,i];
+ *   same for data -> ndata when data != NULL (nchannels columns). */
+int spnb_reorder_data(const float* locs, const float* data, const float* idxs, float* nlocs,
+                      float* ndata, int batch_size, int N, int ndims, int nchannels, int reverse,
+                      void* stream);
+
+/* ---- ConvSP ----------------------------------------------------------------------------------- */
+
+/* Forward.  Replaces cuda_convsp with NULL gradients (gpu_kernels.h:7-33) plus the Python bias add
+ * (convsp.py:172):  out[b,m,o] = bias[o] + sum over neighbours/kernel cells (bias may be NULL). */
+int spnb_convsp_forward(const float* qlocs, const float* locs, const float* data,
+                        const float* neighbors, const float* weight, const float* bias,
+                        int batch_size, int M, int N, int nchannels, int ndims, int max_neighbors,
+                        int nkernels, int ncells, float radius, const float* kernel_size,
+                        const float* dilation, int dis_norm, int kernel_fn, float* out, void* stream);
+
+/* Backward.  Replaces cuda_convsp with non-NULL gradients.  Any of dqlocs/dlocs/ddata/dweight may be
+ * NULL (not computed).  sym_flag: optional device int; when non-NULL, qlocs == locs, and *sym_flag
+ * == 0 at execution time, the neighbour relation is taken to be symmetric and dlocs/ddata are
+ * computed by gathers (no atomics); otherwise the scatter path with float atomics runs.
+ *   workspace: device scratch of spnb_convsp_backward_workspace_bytes() bytes (may be NULL when that
+ *   is 0). */
+size_t spnb_convsp_backward_workspace_bytes(int nkernels, int nchannels, int ncells);
+int spnb_convsp_backward(const float* qlocs, const float* locs, const float* data,
+                         const float* neighbors, const float* weight, int batch_size, int M, int N,
+                         int nchannels, int ndims, int max_neighbors, int nkernels, int ncells,
+                         float radius, const float* kernel_size, const float* dilation, int dis_norm,
+                         int kernel_fn, const float* grad_out, float* dqlocs, float* dlocs,
+                         float* ddata, float* dweight, const int* sym_flag, void* workspace,
+                         void* stream);
+
+/* ---- ConvSDF ---------------------------------------------------------------------------------- */
+
+/* Forward (bias added in the kernel, as common_funcs.h:834-835).  Replaces cuda_convsdf with NULL
+ * gradients (gpu_kernels.h:35-59).  sdfs_len = number of floats in the SDF atlas (bounds guard). */
+int spnb_convsdf_forward(const float* locs, int batch_size, int N, int ndims, const float* idxs,
+                         const float* poses, const float* scales, int M, int pose_len,
+                         const float* sdfs, size_t sdfs_len, const float* sdf_offsets,
+                         const float* sdf_shapes, int nsdfs, const float* weight, const float* bias,
+                         int nkernels, int ncells, const float* kernel_size, const float* dilation,
+                         float max_distance, float* out, void* stream);
+
+/* Backward.  dlocs [B,N,D], dweight [O,ncells], dposes [B,M,pose_len] (translation columns only,
+ * rotation columns are left 0: the reference overwrites them with finite differences in Python,
+ * convsdf.py:211-224).  Any of the three may be NULL. */
+int spnb_convsdf_backward(const float* locs, int batch_size, int N, int ndims, const float* idxs,
+                          const float* poses, const float* scales, int M, int pose_len,
+                          const float* sdfs, size_t sdfs_len, const float* sdf_offsets,
+                          const float* sdf_shapes, int nsdfs, const float* weight, int nkernels,
+                          int ncells, const float* kernel_size, const float* dilation,
+                          float max_distance, const float* grad_out, float* dlocs, float* dweight,
+                          float* dposes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPNB_H_ */

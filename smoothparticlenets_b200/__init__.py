@@ -1,0 +1,20 @@
+"""smoothparticlenets_b200 -- B200 (sm_100a) implementation of the SmoothParticleNets
+particle-interaction hot path, behind the reference's own nn.Module API.
+
+    import smoothparticlenets_b200 as spn
+    coll = spn.ParticleCollision(3, 0.1).cuda()
+    conv = spn.ConvSP(4, 8, 3, 3, 0.05, 0.1, kernel_fn='spiky').cuda()
+
+Exports the same names as ``import SmoothParticleNets as spn`` for this path: ConvSP, ConvSDF,
+ParticleCollision, ReorderData, KERNEL_NAMES, KERNEL_FN (reference python/SmoothParticleNets/
+__init__.py:5-10).  Native code: libspnb.so (C ABI in include/spnb.h), built by
+``python -m smoothparticlenets_b200.build``.  There is no CPU fallback.
+"""
+from .kernels import KERNEL_NAMES, KERNEL_FN, DKERNEL_FN, KERNELS, DKERNELS  # noqa: F401
+from .convsp import ConvSP  # noqa: F401
+from .particlecollision import ParticleCollision, ReorderData  # noqa: F401
+from .convsdf import ConvSDF  # noqa: F401
+from . import error_checking  # noqa: F401
+
+__all__ = ["ConvSP", "ConvSDF", "ParticleCollision", "ReorderData", "KERNEL_NAMES", "KERNEL_FN",
+           "DKERNEL_FN", "KERNELS", "DKERNELS"]

@@ -1,0 +1,644 @@
+// Hash-grid neighbour search for sm_100a: grid bounds, cell keys, a batched stable onesweep radix
+// sort of (cell key, particle index), the ReorderData permutation, the cell table and the
+// fixed-width neighbour lists.
+//
+// Replaces kernel_compute_cellIDs / CUB SortPairs / kernel_fill_cells / kernel_compute_collisions /
+// kernel_reorder_data and their launchers (reference src/gpu_kernels.cu:238-548) and the torch
+// bounds code of ParticleCollision.forward (ParticleCollision.py:174-181).  Semantics follow
+// loc2grid / partial_grid_hash / compute_collisions (src/common_funcs.h:96-119, 875-948).
+//
+// Design notes (DESIGN.md has the byte counts):
+//  * everything is stream-ordered and batched over scenes; the only host-side decisions are grid
+//    sizes that depend on (B, N, D, max_grid_dim);
+//  * the sort is an LSD onesweep: one histogram kernel (fused with key generation) for all digit
+//    places, then one kernel per digit place that ranks a 2048-key tile with warp match/ballot,
+//    obtains its global offsets by decoupled look-back over single-word {flag,count} statuses, and
+//    scatters.  Tiles take tickets from an atomic counter so every predecessor is already running.
+//    Only ceil(log2(ncells+1)) key bits are sorted, split evenly over the passes on the device;
+//  * neighbour lists: one warp per query; the 3^D cells are scanned as ONE concatenated candidate
+//    range (warp prefix sum + per-lane search), hits are compacted with ballot/popc so rows are
+//    written coalesced, including the -1 padding.
+#include "spnb_common.cuh"
+
+namespace spnb {
+
+constexpr int kMaxPasses = 4;
+constexpr int kRadix = 256;
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kSortThreads * kSortItems;
+constexpr uint32_t kFlagAgg = 1u << 30;
+constexpr uint32_t kFlagIncl = 2u << 30;
+constexpr uint32_t kValMask = (1u << 30) - 1;
+
+struct SceneCtl {
+    int ncells;  // prod(grid_dims); keys are 0..ncells-1, ncells marks "outside every cell"
+    int bits;    // key bits to sort
+    int shift[kMaxPasses];
+    int width[kMaxPasses];
+};
+
+struct WsLayout {
+    size_t minmax_off, minmax_bytes;  // uint32 [B][D][2]      (zeroed by spnb_grid_bounds)
+    size_t ctl_off;                   // SceneCtl [B]           (start of the sort control block)
+    size_t err_off;                   // int
+    size_t ticket_off;                // uint32 [kMaxPasses]
+    size_t hist_off;                  // uint32 [B][P][256]
+    size_t status_off;                // uint32 [P][B*tiles][256]
+    size_t ctl_end;                   // end of the block zeroed by spnb_hashgrid_order
+    size_t keys_a_off, keys_b_off, vals_a_off, vals_b_off;  // uint32 [B*N] each
+    size_t total;
+    int passes, tiles;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static WsLayout ws_layout(int B, int N, int D, int G)
+{
+    WsLayout w;
+    double cells = 1.0;
+    for (int k = 0; k < D; ++k) cells *= (double)G;
+    int bits = 1;
+    while (bits < 32 && (double)(1ull << bits) <= cells) ++bits;  // keys 0..cells inclusive
+    w.passes = (bits + 7) / 8;
+    if (w.passes < 1) w.passes = 1;
+    if (w.passes > kMaxPasses) w.passes = kMaxPasses;
+    w.tiles = cdiv(N, kSortTile);
+    size_t off = 0;
+    w.minmax_off = off;
+    w.minmax_bytes = sizeof(uint32_t) * (size_t)B * D * 2;
+    off = align_up(off + w.minmax_bytes, 256);
+    w.ctl_off = off;
+    off = align_up(off + sizeof(SceneCtl) * (size_t)B, 256);
+    w.err_off = off;
+    off += 64;
+    w.ticket_off = off;
+    off = align_up(off + sizeof(uint32_t) * kMaxPasses, 256);
+    w.hist_off = off;
+    off = align_up(off + sizeof(uint32_t) * (size_t)B * w.passes * kRadix, 256);
+    w.status_off = off;
+    off = align_up(off + sizeof(uint32_t) * (size_t)w.passes * B * w.tiles * kRadix, 256);
+    w.ctl_end = off;
+    size_t arr = align_up(sizeof(uint32_t) * (size_t)B * N, 256);
+    w.keys_a_off = off; off += arr;
+    w.keys_b_off = off; off += arr;
+    w.vals_a_off = off; off += arr;
+    w.vals_b_off = off; off += arr;
+    w.total = off;
+    return w;
+}
+
+// ---- grid bounds -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t enc_ordered(float x)
+{
+    uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(uint32_t e)
+{
+    return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
+// acc[b][k][0] = max over particles of ~enc(x) (i.e. the minimum), acc[b][k][1] = max of enc(x).
+__global__ void __launch_bounds__(256) k_bounds_partial(const float* __restrict__ locs, uint32_t* acc,
+                                                        int N, int D)
+{
+    __shared__ uint32_t s_acc[2 * SPNB_MAXD];
+    const int b = blockIdx.y;
+    if (threadIdx.x < 2 * D) s_acc[threadIdx.x] = 0;
+    __syncthreads();
+    const long long total = (long long)N * D;
+    const long long T = (long long)gridDim.x * blockDim.x;
+    const long long S = (T / D) * D;  // stride is a multiple of D so each thread keeps one coordinate
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < S) {
+        const float* p = locs + (size_t)b * total;
+        uint32_t mn = 0, mx = 0;
+        for (long long e = t; e < total; e += S) {
+            uint32_t v = enc_ordered(p[e]);
+            mx = max(mx, v);
+            mn = max(mn, ~v);
+        }
+        const int k = (int)(t % D);
+        if (mx | mn) {
+            atomicMax(&s_acc[2 * k], mn);
+            atomicMax(&s_acc[2 * k + 1], mx);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * D && s_acc[threadIdx.x])
+        atomicMax(&acc[(size_t)b * 2 * D + threadIdx.x], s_acc[threadIdx.x]);
+}
+
+__global__ void k_bounds_final(const uint32_t* acc, float* low, float* grid_dims, int B, int D,
+                               float radius, float max_grid_dim)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * D) return;
+    const float lo = dec_ordered(~acc[2 * i]);
+    const float hi = dec_ordered(acc[2 * i + 1]);
+    float ext = (hi - lo) / radius;
+    ext = fminf(fmaxf(ext, 0.0f), max_grid_dim);
+    const float gd = ceilf(ext);
+    const float center = (lo + hi) / 2;
+    grid_dims[i] = gd;
+    low[i] = center - gd * radius / 2;
+}
+
+// ---- scene control: key range and digit split -------------------------------------------------
+__device__ __forceinline__ int scene_ncells(const float* gd, int D)
+{
+    long long n = 1;
+    for (int k = 0; k < D; ++k) {
+        long long g = (long long)gd[k];
+        if (g <= 0) return 0;
+        n *= g;
+        if (n > 0x3fffffff) return 0x3fffffff;
+    }
+    return (int)n;
+}
+
+__global__ void k_scene_setup(const float* grid_dims, SceneCtl* ctl, int B, int D, int passes)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    SceneCtl c;
+    c.ncells = scene_ncells(grid_dims + b * D, D);
+    int bits = 1;
+    while (bits < 31 && (1u << bits) <= (uint32_t)c.ncells) ++bits;
+    c.bits = bits;
+    const int base = bits / passes, rem = bits % passes;
+    int sh = 0;
+    for (int p = 0; p < kMaxPasses; ++p) {
+        int w = p < passes ? base + (p < rem ? 1 : 0) : 0;
+        c.shift[p] = sh;
+        c.width[p] = w;
+        sh += w;
+    }
+    ctl[b] = c;
+}
+
+// ---- keys + digit histograms for every pass -----------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(kSortThreads)
+k_keys_hist(const float* __restrict__ locs, const float* __restrict__ low,
+            const float* __restrict__ grid_dims, const SceneCtl* __restrict__ ctl,
+            uint32_t* __restrict__ keys, uint32_t* hist, int N, int ndims, float edge, int passes)
+{
+    const int D = DT > 0 ? DT : ndims;
+    __shared__ uint32_t s_hist[kMaxPasses][kRadix];
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const SceneCtl c = ctl[b];
+    float lo[DT > 0 ? DT : SPNB_MAXD], gd[DT > 0 ? DT : SPNB_MAXD];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        lo[k] = low[b * D + k];
+        gd[k] = grid_dims[b * D + k];
+    }
+    const int base = blockIdx.x * kSortTile;
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const int i = base + r * kSortThreads + threadIdx.x;
+        if (i < N) {
+            const float* x = locs + ((size_t)b * N + i) * D;
+            int h = 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) h += hash_term(grid_coord_of(x[k], lo[k], edge), gd, k, D);
+            const uint32_t key = (h < 0 || h >= c.ncells) ? (uint32_t)c.ncells : (uint32_t)h;
+            keys[(size_t)b * N + i] = key;
+            for (int p = 0; p < passes; ++p)
+                atomicAdd(&s_hist[p][(key >> c.shift[p]) & ((1u << c.width[p]) - 1)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
+        const uint32_t v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(&hist[(size_t)b * passes * kRadix + i], v);
+    }
+}
+
+// ---- one onesweep pass --------------------------------------------------------------------------
+// keys_in/vals_in -> keys_out/vals_out, stable by digit `pass`.  vals_in == NULL means "value =
+// position" (first pass); idxs_out != NULL means the values are written as float (last pass).
+__global__ void __launch_bounds__(kSortThreads)
+k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+           uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+           float* __restrict__ idxs_out, const SceneCtl* __restrict__ ctl,
+           const uint32_t* __restrict__ hist, uint32_t* status, uint32_t* ticket, int* err, int B,
+           int N, int tiles, int passes, int pass)
+{
+    constexpr int kWarps = kSortThreads / 32;
+    __shared__ uint32_t s_warp[kWarps][kRadix];  // per-warp digit counts, then exclusive over warps
+    __shared__ uint32_t s_base[kRadix];          // first output slot of each digit for this tile
+    __shared__ uint32_t s_wsum[kWarps];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(&ticket[pass], 1u);
+    for (int i = tid; i < kWarps * kRadix; i += kSortThreads) (&s_warp[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile_g = s_tile;
+    const int b = tile_g / tiles, t = tile_g % tiles;
+    const int shift = ctl[b].shift[pass];
+    const uint32_t mask = (1u << ctl[b].width[pass]) - 1;
+    const size_t sb = (size_t)b * N;
+
+    uint32_t key[kSortItems], rank[kSortItems];
+    const int first = t * kSortTile + warp * 32 * kSortItems + lane;
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const int i = first + r * 32;
+        key[r] = i < N ? keys_in[sb + i] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const bool valid = first + r * 32 < N;
+        const uint32_t digit = valid ? ((key[r] >> shift) & mask) : (uint32_t)kRadix;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = s_warp[warp][digit];
+            s_warp[warp][digit] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = old + __popc(peers & lanemask_lt());
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread `tid` owns digit `tid`
+    uint32_t count = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        const uint32_t c = s_warp[w][tid];
+        s_warp[w][tid] = count;
+        count += c;
+    }
+    // decoupled look-back over the earlier tiles of this scene
+    uint32_t excl = 0;
+    uint32_t* st = status + ((size_t)pass * B * tiles + tile_g) * kRadix + tid;
+    if (t == 0) {
+        st_relaxed(st, kFlagIncl | count);
+    } else {
+        st_relaxed(st, kFlagAgg | count);
+        const uint32_t* sp = st - kRadix;
+        for (int tt = t - 1; tt >= 0; --tt, sp -= kRadix) {
+            uint32_t s;
+            unsigned spins = 0;
+            do {
+                s = ld_relaxed(sp);
+            } while ((s >> 30) == 0 && ++spins < (1u << 27));
+            if ((s >> 30) == 0) {  // never happens with ticket ordering; do not hang if it does
+                *err = 1;
+                break;
+            }
+            excl += s & kValMask;
+            if ((s >> 30) == 2) break;
+        }
+        st_relaxed(st, kFlagIncl | (excl + count));
+    }
+    // exclusive scan of the scene's digit histogram -> first slot of each digit in the scene
+    const uint32_t h = hist[((size_t)b * passes + pass) * kRadix + tid];
+    uint32_t incl = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    uint32_t wpre = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w)
+        if (w < warp) wpre += s_wsum[w];
+    s_base[tid] = wpre + incl - h + excl;
+    __syncthreads();
+
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const int i = first + r * 32;
+        if (i < N) {
+            const uint32_t digit = (key[r] >> shift) & mask;
+            const uint32_t pos = s_base[digit] + s_warp[warp][digit] + rank[r];
+            const uint32_t val = vals_in ? vals_in[sb + i] : (uint32_t)i;
+            keys_out[sb + pos] = key[r];
+            if (idxs_out) idxs_out[sb + pos] = (float)val;
+            else vals_out[sb + pos] = val;
+        }
+    }
+}
+
+// ---- reorder -------------------------------------------------------------------------------------
+// One thread per output float.  reverse == 0: out[b,i,:] = in[b,idxs[b,i],:]; else scatter.
+__global__ void __launch_bounds__(256)
+k_reorder(const float* __restrict__ locs, const float* __restrict__ data,
+          const float* __restrict__ idxs, float* __restrict__ nlocs, float* __restrict__ ndata,
+          long long BN, int N, int D, int C, int reverse)
+{
+    const long long nl = BN * D, total = nl + BN * (long long)C;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const bool is_loc = e < nl;
+        const long long ee = is_loc ? e : e - nl;
+        const int W = is_loc ? D : C;
+        const long long row = ee / W;
+        const int col = (int)(ee - row * W);
+        const long long scene0 = row - row % N;
+        const long long other = scene0 + (long long)idxs[row];
+        const long long src = reverse ? row : other, dst = reverse ? other : row;
+        if (is_loc) nlocs[dst * D + col] = locs[src * D + col];
+        else ndata[dst * C + col] = data[src * C + col];
+    }
+}
+
+// ---- cell table ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_table_clear(const float* __restrict__ grid_dims, float* __restrict__ starts,
+              float* __restrict__ ends, int D, int ncells)
+{
+    const int b = blockIdx.y;
+    int n = scene_ncells(grid_dims + b * D, D);
+    if (n > ncells) n = ncells;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        starts[(size_t)b * ncells + c] = 0.0f;
+        ends[(size_t)b * ncells + c] = 0.0f;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_table_fill(const uint32_t* __restrict__ keys, const float* __restrict__ grid_dims,
+             float* __restrict__ starts, float* __restrict__ ends, int N, int D, int ncells)
+{
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int n = scene_ncells(grid_dims + b * D, D);
+    if (n > ncells) n = ncells;
+    const uint32_t c = keys[(size_t)b * N + i];
+    const uint32_t p = i > 0 ? keys[(size_t)b * N + i - 1] : 0xffffffffu;
+    if (c != p) {
+        if (c < (uint32_t)n) starts[(size_t)b * ncells + c] = (float)i;
+        if (i > 0 && p < (uint32_t)n) ends[(size_t)b * ncells + p] = (float)i;
+    }
+    if (i == N - 1 && c < (uint32_t)n) ends[(size_t)b * ncells + c] = (float)N;
+}
+
+// ---- neighbour lists -----------------------------------------------------------------------------
+// One warp per query.  Cells are visited in the reference's odometer order over {-1,0,1}^D with
+// dimension 0 fastest (common_funcs.h:906,938-943); inside a cell candidates come in sorted order.
+template <int DT>
+__global__ void __launch_bounds__(256)
+k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
+          const float* __restrict__ low, const float* __restrict__ grid_dims,
+          const float* __restrict__ starts, const float* __restrict__ ends,
+          float* __restrict__ coll, int B, int M, int N, int ndims, int K, int ncells, float edge,
+          float r2, int include_self, int* trunc_flag)
+{
+    const int D = DT > 0 ? DT : ndims;
+    constexpr int kWarps = 8;
+    __shared__ int s_off[kWarps][33];
+    __shared__ int s_start[kWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long q = (long long)blockIdx.x * kWarps + warp;
+    if (q >= (long long)B * M) return;
+    const int b = (int)(q / M);
+    const float* x = qlocs + q * D;
+    const float* gd = grid_dims + b * D;
+    float xq[DT > 0 ? DT : SPNB_MAXD];
+    int gc[DT > 0 ? DT : SPNB_MAXD];
+    int total_cells = 1;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        xq[k] = x[k];
+        gc[k] = grid_coord_of(xq[k], low[b * D + k], edge);
+        total_cells *= 3;
+    }
+    float* row = coll + q * K;
+    const float* sl = locs + (size_t)b * N * D;
+    int found = 0;
+
+    for (int cell0 = 0; cell0 < total_cells && found < K; cell0 += 32) {
+        // lane -> one neighbour cell of this chunk
+        const int ci = cell0 + lane;
+        int cnt = 0, cstart = 0;
+        if (ci < total_cells) {
+            int rem = ci, id = 0;
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const int c = gc[k] + (rem % 3) - 1;
+                rem /= 3;
+                if (c < 0 || (float)c >= gd[k]) ok = false;
+                else id += hash_term(c, gd, k, D);
+            }
+            if (ok && id >= 0 && id < ncells) {
+                cstart = (int)starts[(size_t)b * ncells + id];
+                cnt = (int)ends[(size_t)b * ncells + id] - cstart;
+                if (cnt < 0) cnt = 0;
+            }
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        s_off[warp][lane + 1] = incl;
+        if (lane == 0) s_off[warp][0] = 0;
+        s_start[warp][lane] = cstart;
+        __syncwarp();
+
+        for (int base = 0; base < total && found < K; base += 32) {
+            const int t = base + lane;
+            bool hit = false;
+            int idx = 0;
+            if (t < total) {
+                // largest c with s_off[c] <= t  (5-step binary search over 32 entries)
+                int c = 0;
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1)
+                    if (s_off[warp][c + s] <= t) c += s;
+                idx = s_start[warp][c] + (t - s_off[warp][c]);
+                const float* y = sl + (size_t)idx * D;
+                float d = 0.0f;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const float nr = xq[k] - y[k];
+                    d += nr * nr;
+                }
+                hit = d < r2 && (d > 0.0f || include_self);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            const int pos = found + __popc(m & lanemask_lt());
+            if (hit && pos < K) row[pos] = (float)idx;
+            found += __popc(m);
+        }
+    }
+    if (found >= K) {
+        if (trunc_flag && lane == 0) atomicOr(trunc_flag, 1);
+        found = K;
+    }
+    for (int p = found + lane; p < K; p += 32) row[p] = -1.0f;
+}
+
+// ---- launch helpers --------------------------------------------------------------------------------
+static bool valid_common(int B, int N, int D, const char* fn)
+{
+    if (B <= 0 || N <= 0 || D <= 0 || D > SPNB_MAX_NDIM) {
+        set_error("%s: bad sizes batch_size=%d N=%d ndims=%d (need >0, ndims<=%d)", fn, B, N, D,
+                  SPNB_MAX_NDIM);
+        return false;
+    }
+    if (N > (1 << 24)) {
+        set_error("%s: N=%d exceeds 2^24, the float32 index limit of the API", fn, N);
+        return false;
+    }
+    return true;
+}
+
+}  // namespace spnb
+
+using namespace spnb;
+
+extern "C" {
+
+size_t spnb_hashgrid_workspace_bytes(int batch_size, int N, int ndims, int max_grid_dim)
+{
+    if (batch_size <= 0 || N <= 0 || ndims <= 0 || max_grid_dim <= 0) return 0;
+    return ws_layout(batch_size, N, ndims, max_grid_dim).total;
+}
+
+int spnb_grid_bounds(const float* locs, int B, int N, int D, float radius, int max_grid_dim,
+                     float* low, float* grid_dims, void* workspace, size_t workspace_bytes,
+                     void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!valid_common(B, N, D, "spnb_grid_bounds")) return 0;
+    if (!locs || !low || !grid_dims || !workspace) {
+        set_error("spnb_grid_bounds: null pointer");
+        return 0;
+    }
+    const WsLayout w = ws_layout(B, N, D, max_grid_dim);
+    if (workspace_bytes < w.total) {
+        set_error("spnb_grid_bounds: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+        return 0;
+    }
+    uint32_t* acc = (uint32_t*)((char*)workspace + w.minmax_off);
+    cudaMemsetAsync(acc, 0, w.minmax_bytes, stream);
+    int bx = cdiv((long long)N * D, 256 * 8);
+    if (bx > 148 * 4) bx = 148 * 4;
+    if (bx < 1) bx = 1;
+    while ((long long)bx * 256 < D) ++bx;
+    k_bounds_partial<<<dim3(bx, B), 256, 0, stream>>>(locs, acc, N, D);
+    k_bounds_final<<<cdiv(B * D, 128), 128, 0, stream>>>(acc, low, grid_dims, B, D, radius,
+                                                         (float)max_grid_dim);
+    return check_launch("spnb_grid_bounds") ? 1 : 0;
+}
+
+int spnb_hashgrid_order(const float* locs, const float* low, const float* grid_dims, float* cellIDs,
+                        float* idxs, void* workspace, size_t workspace_bytes, int B, int N, int D,
+                        float cellEdge, int max_grid_dim, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!valid_common(B, N, D, "spnb_hashgrid_order")) return 0;
+    if (!locs || !low || !grid_dims || !cellIDs || !idxs || !workspace) {
+        set_error("spnb_hashgrid_order: null pointer");
+        return 0;
+    }
+    const WsLayout w = ws_layout(B, N, D, max_grid_dim);
+    if (workspace_bytes < w.total) {
+        set_error("spnb_hashgrid_order: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+        return 0;
+    }
+    char* ws = (char*)workspace;
+    SceneCtl* ctl = (SceneCtl*)(ws + w.ctl_off);
+    int* err = (int*)(ws + w.err_off);
+    uint32_t* ticket = (uint32_t*)(ws + w.ticket_off);
+    uint32_t* hist = (uint32_t*)(ws + w.hist_off);
+    uint32_t* status = (uint32_t*)(ws + w.status_off);
+    uint32_t* kbuf[2] = {(uint32_t*)(ws + w.keys_a_off), (uint32_t*)(ws + w.keys_b_off)};
+    uint32_t* vbuf[2] = {(uint32_t*)(ws + w.vals_a_off), (uint32_t*)(ws + w.vals_b_off)};
+
+    cudaMemsetAsync(ws + w.ctl_off, 0, w.ctl_end - w.ctl_off, stream);
+    k_scene_setup<<<cdiv(B, 128), 128, 0, stream>>>(grid_dims, ctl, B, D, w.passes);
+    const dim3 tg(w.tiles, B);
+    switch (D) {
+    case 1: k_keys_hist<1><<<tg, kSortThreads, 0, stream>>>(locs, low, grid_dims, ctl, kbuf[0], hist, N, D, cellEdge, w.passes); break;
+    case 2: k_keys_hist<2><<<tg, kSortThreads, 0, stream>>>(locs, low, grid_dims, ctl, kbuf[0], hist, N, D, cellEdge, w.passes); break;
+    case 3: k_keys_hist<3><<<tg, kSortThreads, 0, stream>>>(locs, low, grid_dims, ctl, kbuf[0], hist, N, D, cellEdge, w.passes); break;
+    default: k_keys_hist<0><<<tg, kSortThreads, 0, stream>>>(locs, low, grid_dims, ctl, kbuf[0], hist, N, D, cellEdge, w.passes); break;
+    }
+    for (int p = 0; p < w.passes; ++p) {
+        const bool last = p == w.passes - 1;
+        const uint32_t* kin = kbuf[p & 1];
+        const uint32_t* vin = p == 0 ? nullptr : vbuf[p & 1];
+        uint32_t* kout = last ? (uint32_t*)cellIDs : kbuf[(p + 1) & 1];
+        uint32_t* vout = last ? nullptr : vbuf[(p + 1) & 1];
+        k_onesweep<<<w.tiles * B, kSortThreads, 0, stream>>>(kin, vin, kout, vout,
+                                                             last ? idxs : nullptr, ctl, hist, status,
+                                                             ticket, err, B, N, w.tiles, w.passes, p);
+    }
+    return check_launch("spnb_hashgrid_order") ? 1 : 0;
+}
+
+int spnb_reorder_data(const float* locs, const float* data, const float* idxs, float* nlocs,
+                      float* ndata, int B, int N, int D, int C, int reverse, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (B <= 0 || N <= 0 || D <= 0) {
+        set_error("spnb_reorder_data: bad sizes");
+        return 0;
+    }
+    if (!locs || !idxs || !nlocs || (data && !ndata)) {
+        set_error("spnb_reorder_data: null pointer");
+        return 0;
+    }
+    if (!data) C = 0;
+    const long long BN = (long long)B * N;
+    int blocks = cdiv(BN * (D + C), 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    k_reorder<<<blocks, 256, 0, stream>>>(locs, data, idxs, nlocs, ndata, BN, N, D, C, reverse);
+    return check_launch("spnb_reorder_data") ? 1 : 0;
+}
+
+int spnb_compute_collisions(const float* qlocs, const float* locs, const float* low,
+                            const float* grid_dims, const float* cellIDs, float* cellStarts,
+                            float* cellEnds, float* collisions, int B, int M, int N, int D, int K,
+                            int ncells, float cellEdge, float radius, int include_self,
+                            int* trunc_flag, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!valid_common(B, N, D, "spnb_compute_collisions")) return 0;
+    if (M <= 0 || K <= 0 || ncells <= 0) {
+        set_error("spnb_compute_collisions: bad sizes M=%d max_collisions=%d ncells=%d", M, K, ncells);
+        return 0;
+    }
+    if (!qlocs || !locs || !low || !grid_dims || !cellIDs || !cellStarts || !cellEnds || !collisions) {
+        set_error("spnb_compute_collisions: null pointer");
+        return 0;
+    }
+    k_table_clear<<<dim3(148, B), 256, 0, stream>>>(grid_dims, cellStarts, cellEnds, D, ncells);
+    k_table_fill<<<dim3(cdiv(N, 256), B), 256, 0, stream>>>((const uint32_t*)cellIDs, grid_dims,
+                                                            cellStarts, cellEnds, N, D, ncells);
+    const float r2 = radius * radius;
+    const int blocks = cdiv((long long)B * M, 8);
+#define SPNB_COLLIDE(DT)                                                                          \
+    k_collide<DT><<<blocks, 256, 0, stream>>>(qlocs, locs, low, grid_dims, cellStarts, cellEnds,   \
+                                              collisions, B, M, N, D, K, ncells, cellEdge, r2,     \
+                                              include_self, trunc_flag)
+    switch (D) {
+    case 1: SPNB_COLLIDE(1); break;
+    case 2: SPNB_COLLIDE(2); break;
+    case 3: SPNB_COLLIDE(3); break;
+    default: SPNB_COLLIDE(0); break;
+    }
+#undef SPNB_COLLIDE
+    return check_launch("spnb_compute_collisions") ? 1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,188 @@
+"""ParticleCollision and ReorderData on libspnb (sm_100a).
+
+Drop-in for python/SmoothParticleNets/ParticleCollision.py of the reference: same constructors,
+registered buffer names (cellIDs, cellStarts, cellEnds, cuda_buffer), return tuples and autograd
+semantics (only the reorder pass-through carries gradients, ParticleCollision.py:238-243,
+277-283, 303-314).  The whole forward is stream-ordered: bounds, cell hash, stable sort, reorder,
+cell table and neighbour lists run without a host synchronisation.
+"""
+import numbers  # noqa: F401
+
+import torch
+
+from . import _native as nat
+from . import error_checking as ec
+from .convsp import nat_max_dim
+
+
+class ReorderData(torch.nn.Module):
+    """reverse=False: ret = input[idxs];  reverse=True: ret[idxs] = input
+    (reference ParticleCollision.py:13-58)."""
+
+    def __init__(self, reverse=False):
+        super(ReorderData, self).__init__()
+        self.reverse = (1 if reverse else 0)
+
+    def forward(self, idxs, locs, data=None):
+        batch_size = locs.size()[0]
+        N = locs.size()[1]
+        ec.check_tensor_dims(locs, "locs", (batch_size, N, -1))
+        ec.check_tensor_dims(idxs, "idxs", (batch_size, N))
+        if data is not None:
+            ec.check_tensor_dims(data, "data", (batch_size, N, -1))
+            data = data.contiguous()
+        locs = locs.contiguous()
+        idxs = idxs.contiguous()
+        nlocs, ndata = _ReorderDataFunction.apply(idxs, locs, data, self.reverse)
+        if data is None:
+            return nlocs
+        return nlocs, ndata
+
+
+def _reorder(idxs, locs, data, reverse):
+    nat.require_cuda_f32(idxs, "idxs")
+    nat.require_cuda_f32(locs, "locs")
+    B, N, D = locs.shape
+    nlocs = torch.empty_like(locs)
+    ndata = None
+    C = 0
+    if data is not None:
+        nat.require_cuda_f32(data, "data")
+        C = data.shape[2]
+        ndata = torch.empty_like(data)
+    with torch.cuda.device(locs.device):
+        nat.check(nat.lib().spnb_reorder_data(nat.ptr(locs), nat.ptr(data), nat.ptr(idxs),
+                                              nat.ptr(nlocs), nat.ptr(ndata), B, N, D, C,
+                                              int(reverse), nat.stream()), "spnb_reorder_data")
+    return nlocs, ndata
+
+
+class _ReorderDataFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, idxs, locs, data, reverse):
+        ctx.save_for_backward(idxs)
+        ctx.reverse = reverse
+        ctx.has_data = data is not None
+        nlocs, ndata = _reorder(idxs, locs, data, reverse)
+        if ndata is None:
+            ndata = locs.new_empty(0)
+            ctx.mark_non_differentiable(ndata)
+        return nlocs, ndata
+
+    @staticmethod
+    def backward(ctx, grad_locs, grad_data):
+        idxs, = ctx.saved_tensors
+        gd = grad_data.contiguous() if ctx.has_data else None
+        glocs, gdata = _reorder(idxs, grad_locs.contiguous(), gd, 1 - ctx.reverse)
+        return None, glocs, gdata, None
+
+
+class ParticleCollision(torch.nn.Module):
+    """Hash-grid neighbour search (reference ParticleCollision.py:61-203)."""
+
+    def __init__(self, ndim, radius, max_grid_dim=96, max_collisions=128, include_self=True):
+        super(ParticleCollision, self).__init__()
+        self.ndim = ec.check_conditions(ndim, "ndim", "%s > 0", "%s < " + str(nat_max_dim()),
+                                        "isinstance(%s, numbers.Integral)")
+        self.radius = ec.check_conditions(radius, "radius", "%s >= 0",
+                                          "isinstance(%s, numbers.Real)")
+        self.max_grid_dim = ec.check_conditions(max_grid_dim, "max_grid_dim", "%s > 0",
+                                                "isinstance(%s, numbers.Integral)")
+        self.max_collisions = ec.check_conditions(max_collisions, "max_collisions", "%s > 0",
+                                                  "isinstance(%s, numbers.Integral)")
+        self.include_self = 1 if include_self else 0
+        self.radixsort_buffer_size = -1
+        # Same buffer names as the reference (ParticleCollision.py:97-100) so state_dicts load.
+        # cellStarts/cellEnds are allocated lazily at [B, max_grid_dim**ndim] on first use.
+        self.register_buffer("cellIDs", torch.zeros(1, 1))
+        self.register_buffer("cellStarts", torch.zeros(1, 1))
+        self.register_buffer("cellEnds", torch.zeros(1, 1))
+        self.register_buffer("cuda_buffer", torch.zeros(1,))
+        self.reorder = ReorderData(reverse=False)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # The four buffers are scratch: accept whatever shape a checkpoint carries.
+        for name in ("cellIDs", "cellStarts", "cellEnds", "cuda_buffer"):
+            key = prefix + name
+            if key in state_dict:
+                getattr(self, name).resize_(state_dict[key].shape)
+        super(ParticleCollision, self)._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def _scratch(self, name, shape, device):
+        buf = getattr(self, name)
+        if buf.device != device or tuple(buf.shape) != tuple(shape):
+            buf = torch.empty(shape, device=device, dtype=torch.float32)
+            setattr(self, name, buf)
+        return buf
+
+    def forward(self, locs, data=None, qlocs=None):
+        """Returns (locs, [data], idxs, neighbors) exactly as the reference
+        (ParticleCollision.py:104-203): locs/data reordered by hash-grid cell, idxs[b,i] = original
+        index of the particle now at i, neighbors BxMxK float lists terminated by -1."""
+        batch_size = locs.size()[0]
+        N = locs.size()[1]
+        ec.check_tensor_dims(locs, "locs", (batch_size, N, self.ndim))
+        has_data = data is not None
+        if has_data:
+            ec.check_tensor_dims(data, "data", (batch_size, N, -1))
+            data = data.contiguous()
+        if qlocs is not None:
+            ec.check_tensor_dims(qlocs, "qlocs", (batch_size, -1, self.ndim))
+            qlocs = qlocs.contiguous()
+        locs = locs.contiguous()
+        nat.require_cuda_f32(locs, "locs")
+        dev = locs.device
+        L = nat.lib()
+        D, G = self.ndim, self.max_grid_dim
+        ncells = G ** D
+
+        ws_bytes = L.spnb_hashgrid_workspace_bytes(batch_size, N, D, G)
+        self.radixsort_buffer_size = ws_bytes
+        ws = self._scratch("cuda_buffer", ((ws_bytes + 3) // 4,), dev)
+        cellIDs = self._scratch("cellIDs", (batch_size + 2, N, 1), dev)
+        cellStarts = self._scratch("cellStarts", (batch_size, ncells), dev)
+        cellEnds = self._scratch("cellEnds", (batch_size, ncells), dev)
+
+        with torch.no_grad(), torch.cuda.device(dev):
+            st = nat.stream()
+            ld = locs.detach()
+            lower_bounds = torch.empty(batch_size, D, device=dev, dtype=torch.float32)
+            grid_dims = torch.empty(batch_size, D, device=dev, dtype=torch.float32)
+            nat.check(L.spnb_grid_bounds(nat.ptr(ld), batch_size, N, D, float(self.radius), G,
+                                         nat.ptr(lower_bounds), nat.ptr(grid_dims), nat.ptr(ws),
+                                         ws_bytes, st), "spnb_grid_bounds")
+            idxs = torch.empty(batch_size, N, device=dev, dtype=torch.float32)
+            nat.check(L.spnb_hashgrid_order(nat.ptr(ld), nat.ptr(lower_bounds), nat.ptr(grid_dims),
+                                            nat.ptr(cellIDs), nat.ptr(idxs), nat.ptr(ws), ws_bytes,
+                                            batch_size, N, D, float(self.radius), G, st),
+                      "spnb_hashgrid_order")
+
+        # Reorder locs (and data) -- the only differentiable step.
+        if has_data:
+            locs, data = self.reorder(idxs, locs, data)
+        else:
+            locs = self.reorder(idxs, locs)
+
+        with torch.no_grad(), torch.cuda.device(dev):
+            q = locs.detach() if qlocs is None else qlocs.detach()
+            nat.require_cuda_f32(q, "qlocs")
+            M = q.shape[1]
+            neighbors = torch.empty(batch_size, M, self.max_collisions, device=dev,
+                                    dtype=torch.float32)
+            trunc = torch.zeros(1, device=dev, dtype=torch.int32)
+            nat.check(L.spnb_compute_collisions(
+                nat.ptr(q), nat.ptr(locs.detach()), nat.ptr(lower_bounds), nat.ptr(grid_dims),
+                nat.ptr(cellIDs), nat.ptr(cellStarts), nat.ptr(cellEnds), nat.ptr(neighbors),
+                batch_size, M, N, D, self.max_collisions, ncells, float(self.radius),
+                float(self.radius), self.include_self, nat.ptr(trunc), nat.stream()),
+                "spnb_compute_collisions")
+        if qlocs is None:
+            # Lists built with the particles as their own queries are symmetric unless one was cut
+            # at max_collisions; ConvSP's backward uses this to avoid atomics.
+            neighbors._spnb_sym_flag = trunc
+        self.last_lower_bounds = lower_bounds
+        self.last_grid_dims = grid_dims
+        if has_data:
+            return locs, data, idxs, neighbors
+        return locs, idxs, neighbors

@@ -1,0 +1,174 @@
+"""GPU parity: hash-grid neighbour search through the C ABI.
+
+Bar: bit-exact.  Grid bounds, cell keys, the stable (key, index) order, reordered rows, and the
+neighbour rows incl. order, truncation at K and -1 padding must equal the oracle's on the same
+inputs.  The CPU reference's own selection sort is unstable, so -- as prescribed
+there -- the permutation is compared with the stable contract of the reference GPU path
+(oracle.hashgrid_order(stable=True)) and the downstream stages are checked by feeding OUR
+permutation to the oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import gpu_util as gu
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # B, N, M, D, C, extent, radius, G
+    (2, 100, 77, 2, 2, 1.0, 0.2, 96),      # tests/test_particlecollision.py shape
+    (3, 257, 50, 1, 1, 2.3, 0.037, 96),
+    (3, 1000, 333, 3, 3, 1.0, 0.1, 96),
+    (2, 5000, 100, 3, 4, 1.0, 0.05, 96),   # 20^3 cells
+    (1, 4099, 64, 3, 2, 4.0, 0.03, 16),    # extent clamps: many particles in border cells
+    (2, 3000, 10, 2, 2, 1.0, 0.01, 96),    # 3 sort passes' worth of bits in 2-D (96^2 cells)
+    (1, 1, 1, 3, 1, 1.0, 0.1, 96),         # single particle: degenerate grid (grid_dims == 0)
+    (2, 40, 7, 4, 2, 1.0, 0.3, 8),         # runtime-ndims path
+]
+
+
+@pytest.mark.parametrize("B,N,M,D,C,extent,radius,G", CASES)
+def test_search_pipeline_bit_exact(spn, oracle, B, N, M, D, C, extent, radius, G):
+    locs, qlocs, data = cases.collision_case(1, B=B, N=N, M=M, D=D, C=C, extent=extent)
+    lt, qt, dt = gu.dev(locs), gu.dev(qlocs), gu.dev(data)
+
+    # a1 bounds
+    low, gd = gu.grid_bounds(lt, radius, G)
+    o_low, o_gd = oracle.grid_bounds(locs, radius, G)
+    gu.assert_bit_equal(gu.host(gd), o_gd, "grid_dims")
+    gu.assert_bit_equal(gu.host(low), o_low, "lower_bounds")
+
+    # a2 + a3 keys and stable order
+    ids, idxs = gu.hashgrid_order(lt, low, gd, radius, G)
+    o_ids, o_idxs = oracle.hashgrid_order(locs, o_low, o_gd, radius, stable=True)
+    degenerate = bool((o_gd == 0).any())
+    got_ids = gu.host(ids).view(np.uint32).astype(np.int64)
+    if not degenerate:
+        assert np.array_equal(got_ids, o_ids.astype(np.int64)), "sorted cell keys"
+        gu.assert_bit_equal(gu.host(idxs), o_idxs, "idxs")
+    else:
+        # every key is "outside all cells": order must stay the identity (stable)
+        assert np.array_equal(gu.host(idxs), np.tile(np.arange(N, dtype=np.float32), (B, 1)))
+    my_idxs = gu.host(idxs)
+    for b in range(B):
+        assert np.array_equal(np.sort(my_idxs[b]), np.arange(N)), "idxs is a permutation"
+
+    # a4 reorder, both directions
+    nl, nd = gu.reorder(lt, dt, idxs, 0)
+    o_nl, o_nd = oracle.reorder_data(locs, data, my_idxs, 0)
+    gu.assert_bit_equal(gu.host(nl), o_nl, "reordered locs")
+    gu.assert_bit_equal(gu.host(nd), o_nd, "reordered data")
+    rl, rd = gu.reorder(nl, nd, idxs, 1)
+    gu.assert_bit_equal(gu.host(rl), locs, "reverse reorder restores locs")
+    gu.assert_bit_equal(gu.host(rd), data, "reverse reorder restores data")
+    only_l, none = gu.reorder(lt, None, idxs, 0)
+    gu.assert_bit_equal(gu.host(only_l), o_nl, "reorder without data")
+
+    if degenerate:
+        coll, _ = gu.collisions(qt, nl, low, gd, ids, radius, radius, 8, 1, G)
+        assert np.all(gu.host(coll) == -1), "degenerate grid finds nothing (oracle behaviour)"
+        return
+
+    # a5 + a6 neighbour rows
+    sorted_ids_f = got_ids.astype(np.float32)
+    for include_self in (0, 1):
+        for K in (4, 128):
+            for q_np, q_t in ((qlocs, qt), (o_nl, nl)):
+                coll, flag = gu.collisions(q_t, nl, low, gd, ids, radius, radius, K, include_self, G)
+                o_coll, _, _ = oracle.compute_collisions(q_np, o_nl, o_low, o_gd, sorted_ids_f, radius,
+                                                         radius, K, include_self, G ** D)
+                # oracle leaves entries after the terminator at their -1 pre-fill: full rows compare
+                gu.assert_bit_equal(gu.host(coll), o_coll, "neighbour rows K=%d self=%d" % (K, include_self))
+                full = bool((o_coll[..., K - 1] >= 0).any())
+                assert bool(flag.item()) == full, "truncation flag"
+
+
+def test_module_api_reference_test_shape(spn, oracle):
+    """tests/test_particlecollision.py:36-122 re-run against the drop-in modules."""
+    B, N, M, D, R, C = 2, 100, 77, 2, 0.2, 2
+    locs, qlocs, data = cases.collision_case(0, B=B, N=N, M=M, D=D, C=C)
+    gt = np.ones((B, M, N), dtype=int) * -1
+    for b in range(B):
+        for i in range(M):
+            d = np.square(qlocs[b, i][None] - locs[b]).sum(1)
+            js = np.where(d <= R * R)[0]
+            gt[b, i, :len(js)] = js
+    lt, qt, dt = gu.dev(locs), gu.dev(qlocs), gu.dev(data)
+    coll = spn.ParticleCollision(D, R, max_collisions=N).cuda()
+    vlocs, vdata, vidxs, vneighbors = coll(lt, dt, qt)
+    idxs = gu.host(vidxs).astype(int)
+    nb = gu.host(vneighbors).astype(int)
+    for b in range(B):
+        assert sorted(idxs[b]) == list(range(N))
+        assert np.array_equal(locs[b][idxs[b]], gu.host(vlocs)[b])
+        assert np.array_equal(data[b][idxs[b]], gu.host(vdata)[b])
+    assert np.array_equal(gu.host(lt), locs) and np.array_equal(gu.host(dt), data)
+    for b in range(B):
+        for i in range(M):
+            mine = set(idxs[b][j] for j in nb[b, i] if j >= 0)
+            want = set(j for j in gt[b, i] if j >= 0)
+            assert mine == want
+    reorder = spn.ReorderData(reverse=True).cuda()
+    rl, rd = reorder(vidxs, vlocs, vdata)
+    assert np.array_equal(gu.host(rl), locs) and np.array_equal(gu.host(rd), data)
+    # no-data / no-qlocs return arities
+    out = coll(lt)
+    assert len(out) == 3 and out[2].shape == (B, N, N)
+    assert hasattr(out[2], "_spnb_sym_flag")
+
+
+def test_reorder_gradient_is_inverse_permutation(spn):
+    """_ReorderDataFunction.backward (ParticleCollision.py:303-314): grads flow back through the
+    inverse permutation; collisions/hash order contribute nothing."""
+    B, N, D, C = 2, 64, 3, 2
+    locs, _, data = cases.collision_case(3, B=B, N=N, M=1, D=D, C=C)
+    lt = gu.dev(locs).requires_grad_(True)
+    dt = gu.dev(data).requires_grad_(True)
+    coll = spn.ParticleCollision(D, 0.3).cuda()
+    sl, sd, idxs, nb = coll(lt, dt)
+    gl = torch.rand_like(sl)
+    gdd = torch.rand_like(sd)
+    (sl * gl).sum().backward(retain_graph=True)
+    (sd * gdd).sum().backward()
+    ii = gu.host(idxs).astype(int)
+    want_l = np.zeros_like(locs)
+    want_d = np.zeros_like(data)
+    for b in range(B):
+        want_l[b][ii[b]] = gu.host(gl)[b]
+        want_d[b][ii[b]] = gu.host(gdd)[b]
+    gu.assert_bit_equal(gu.host(lt.grad), want_l, "dlocs")
+    gu.assert_bit_equal(gu.host(dt.grad), want_d, "ddata")
+
+
+def test_full_size_properties(spn):
+    """BASELINE.json config 2 size (8 x 65536, D=3, r=0.1): size-independent properties --
+    sortedness, permutation validity, reorder round trip, neighbour symmetry and distances."""
+    B, N, R, K = 8, 65536, 0.1, 128
+    locs, vel, L = cases.fluid_cloud(0, B, N)
+    lt, vt = gu.dev(locs), gu.dev(vel)
+    coll = spn.ParticleCollision(3, R, max_collisions=K, include_self=False).cuda()
+    sl, sv, idxs, nb = coll(lt, vt)
+    keys = coll.cellIDs[:B].view(torch.int32).view(B, N)
+    assert bool((keys[:, 1:] >= keys[:, :-1]).all()), "keys sorted"
+    assert bool((idxs.sort(1).values == torch.arange(N, device="cuda", dtype=torch.float32)).all())
+    rl, rv = spn.ReorderData(reverse=True)(idxs, sl, sv)
+    assert torch.equal(rl, lt) and torch.equal(rv, vt)
+    # stable: within equal keys the original indices ascend
+    same = keys[:, 1:] == keys[:, :-1]
+    assert bool((idxs[:, 1:][same] > idxs[:, :-1][same]).all()), "ties by ascending original index"
+    assert int(nb._spnb_sym_flag.item()) == 0
+    cnt = (nb >= 0).sum(2)
+    assert 20 < float(cnt.float().mean()) < 40, "n-bar ~ 30 at this density"
+    # every listed neighbour is within the radius, none is the particle itself
+    b = 3
+    j = nb[b].long().clamp(min=0)
+    d2 = ((sl[b][:, None, :] - sl[b][j]) ** 2).sum(2)
+    valid = nb[b] >= 0
+    assert bool((d2[valid] < R * R).all()) and bool((d2[valid] > 0).all())
+    # symmetry of the relation: i in list(j) <=> j in list(i), checked through degree sums
+    deg_out = valid.sum(1)
+    deg_in = torch.zeros(N, device="cuda", dtype=torch.long).index_add_(
+        0, j[valid], torch.ones(int(valid.sum()), device="cuda", dtype=torch.long))
+    assert torch.equal(deg_in, deg_out)
