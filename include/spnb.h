@@ -38,6 +38,10 @@ const char* spnb_last_error(void);
 /* Replaces spn_max_cartesian_dim (cpu_layer_funcs.cpp:29-32). */
 int spnb_max_cartesian_dim(void);
 
+/* Number of CUDA kernels this process has enqueued through the library so far (host-side counter;
+ * bench accounting, no reference counterpart). */
+unsigned long long spnb_launch_count(void);
+
 /* ---- hash-grid neighbour search ------------------------------------------------------------- */
 
 /* Bytes of device scratch needed by spnb_grid_bounds / spnb_hashgrid_order for these sizes.

@@ -18,6 +18,7 @@ _SIGNATURES = {
     "spnb_version": (ctypes.c_int, []),
     "spnb_last_error": (ctypes.c_char_p, []),
     "spnb_max_cartesian_dim": (ctypes.c_int, []),
+    "spnb_launch_count": (ctypes.c_ulonglong, []),
     "spnb_hashgrid_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "spnb_grid_bounds": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "spnb_hashgrid_order": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _i, _vp]),

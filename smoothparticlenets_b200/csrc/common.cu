@@ -21,6 +21,10 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+
+void count_launches(int n) { g_launches += (unsigned long long)n; }
+
 bool check_launch(const char* what)
 {
     cudaError_t e = cudaGetLastError();
@@ -102,5 +106,6 @@ extern "C" {
 int spnb_version(void) { return 100; }
 const char* spnb_last_error(void) { return spnb::g_err; }
 int spnb_max_cartesian_dim(void) { return SPNB_MAX_NDIM + 1; }
+unsigned long long spnb_launch_count(void) { return spnb::g_launches; }
 
 }  // extern "C"

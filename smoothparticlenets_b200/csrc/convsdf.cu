@@ -364,6 +364,7 @@ static int launch_convsdf(const float* locs, int B, int N, const float* idxs, co
         locs, N, idxs, poses, scales, S, pose_len, sdfs, (long long)sdfs_len, sdf_offsets,
         sdf_shapes, nsdfs, weight, bias, O, ncells, ksize, dil, max_distance, out, go, dlocs,
         dweight, dposes, dw_in_smem);
+    count_launches(1);
     return check_launch(BWD ? "spnb_convsdf_backward" : "spnb_convsdf_forward") ? 1 : 0;
 }
 

@@ -8,28 +8,22 @@
 // step, the four groups of a warp read four rows, and the per-query sums are finished with log2(G)
 // shuffles.  The list is consumed up to the first negative entry, as the reference does.
 //
-//  * k_convsp_fwd_small / k_convsp_bwd_small: ncells == 1 (kernel_size all 1) with compile-time
-//    channel counts; weights, data rows and accumulators live in registers.  These are the
-//    fluid-simulation layers (examples/fluid_sim.py:156-175).  The backward kernel has an
-//    atomics-free mode: when the neighbour relation is symmetric (qlocs is locs, lists not
-//    truncated), d(loss)/d(locs[j]) and d(loss)/d(data[j]) are GATHERED over j's own list instead of
-//    scattered with atomics.
-//  * k_convsp_fwd_generic / k_convsp_bwd_generic: any ndims / channels / kernel_size.
-//
-// Per-term arithmetic keeps the reference's association ((w*data)*W)*norm and its float/double
-// promotions, so individual terms are bit-identical to the CPU reference and only the summation
-// order differs (-fmad=false; see spnb_common.cuh).
+//  * convsp_small.cu: ncells == 1 (kernel_size all 1) with compile-time channel counts -- the
+//    fluid-simulation layers (examples/fluid_sim.py:156-175).  Its backward has an atomics-free
+//    mode: when the neighbour relation is symmetric (qlocs is locs, lists not truncated),
+//    d(loss)/d(locs[j]) and d(loss)/d(data[j]) are GATHERED over j's own list instead of scattered
+//    with atomics.
+//  * this file: k_convsp_fwd_generic / k_convsp_bwd_generic for any ndims / channels /
+//    kernel_size, and the C ABI.  Here per-term arithmetic keeps the reference's association
+//    ((w*data)*W)*norm and its float/double promotions, so individual terms are bit-identical to
+//    the CPU reference and only the summation order differs (-fmad=false; see spnb_common.cuh).
+#include "convsp_small.cuh"
 #include "spnb_common.cuh"
 
 namespace spnb {
 
 constexpr int kG = 8;  // lanes per query
 constexpr int kThreads = 256;
-
-struct ConvGeom {
-    float rad2;   // radius*radius
-    float cull2;  // (radius + (max ksize/2)*max dil*fastroot(D))^2, common_funcs.h:481-485
-};
 
 // First negative entry among the G lanes of my group (G if none) from a warp ballot of "negative".
 __device__ __forceinline__ int group_first_neg(unsigned neg, int lane, int sub)
@@ -44,256 +38,6 @@ __device__ __forceinline__ T group_sum(T v)
 #pragma unroll
     for (int o = kG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-
-// =================================================================================================
-// ncells == 1 fast path
-// =================================================================================================
-template <int D, int C, int O>
-__global__ void __launch_bounds__(kThreads)
-k_convsp_fwd_small(const float* __restrict__ qlocs, const float* __restrict__ locs,
-                   const float* __restrict__ data, const float* __restrict__ neighbors,
-                   const float* __restrict__ weight, const float* __restrict__ bias,
-                   long long BM, int M, int N, int K, float rad2, int dis_norm, SphParams sp,
-                   float* __restrict__ out)
-{
-    const int lane = threadIdx.x & 31, sub = lane & (kG - 1);
-    const long long q = ((long long)blockIdx.x * kThreads + threadIdx.x) / kG;
-    const bool active = q < BM;
-    const long long qq = active ? q : 0;
-    const int b = (int)(qq / M);
-    float w[O * C];
-#pragma unroll
-    for (int i = 0; i < O * C; ++i) w[i] = weight[i];
-    float x[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) x[k] = qlocs[qq * D + k];
-    const float* row = neighbors + qq * K;
-    const float* sl = locs + (size_t)b * N * D;
-    const float* sd = data + (size_t)b * N * C;
-    float acc[O];
-#pragma unroll
-    for (int o = 0; o < O; ++o) acc[o] = 0.0f;
-
-    for (int jj0 = 0; jj0 < K; jj0 += kG) {
-        const int jj = jj0 + sub;
-        const float nb = (active && jj < K) ? row[jj] : -1.0f;
-        const unsigned neg = __ballot_sync(0xffffffffu, !(nb >= 0.0f));
-        const int fneg = group_first_neg(neg, lane, sub);
-        if (sub < fneg) {
-            const int j = (int)nb;
-            const float* y = sl + (size_t)j * D;
-            float d = 0.0f;
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const float nr = x[k] - y[k];
-                d += nr * nr;
-            }
-            if (d < rad2) {
-                d = sqrtf(d);
-                float norm = 1.0f;
-                if (dis_norm && d > 0.0f) norm /= d;
-                const float kw = d > sp.H ? 0.0f : sph_eval(sp.w_expr, d, sp.H, sp.w_coef);
-                float dj[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) dj[c] = sd[(size_t)j * C + c];
-#pragma unroll
-                for (int o = 0; o < O; ++o)
-#pragma unroll
-                    for (int c = 0; c < C; ++c) acc[o] += w[o * C + c] * dj[c] * kw * norm;
-            }
-        }
-        if (__all_sync(0xffffffffu, fneg < kG)) break;
-    }
-#pragma unroll
-    for (int o = 0; o < O; ++o) acc[o] = group_sum(acc[o]);
-    if (active && sub == 0) {
-#pragma unroll
-        for (int o = 0; o < O; ++o) out[q * O + o] = acc[o] + (bias ? bias[o] : 0.0f);
-    }
-}
-
-// Backward, ncells == 1.  `go` = grad_output [B,M,O].
-//   dq (may be NULL): [B,M,D], written by the owning group.
-//   dl, dd (may be NULL): [B,N,D], [B,N,C].  Symmetric mode: written by the owning group (gather);
-//   otherwise accumulated with atomics into zero-filled buffers.
-//   dw (may be NULL): [O,C] accumulated with atomics (zero-filled by the launcher).
-//   same_q_l: dq and dl are the same buffer (qlocs is locs): the sum is produced.
-template <int D, int C, int O>
-__global__ void __launch_bounds__(kThreads)
-k_convsp_bwd_small(const float* __restrict__ qlocs, const float* __restrict__ locs,
-                   const float* __restrict__ data, const float* __restrict__ neighbors,
-                   const float* __restrict__ weight, const float* __restrict__ go,
-                   long long BM, int M, int N, int K, float rad2, int dis_norm, SphParams sp,
-                   float* dq, float* dl, float* dd, float* dw, const int* sym_flag, int same_q_l)
-{
-    __shared__ float s_dw[O * C];
-    const bool sym = sym_flag != nullptr && *sym_flag == 0;
-    const int lane = threadIdx.x & 31, sub = lane & (kG - 1);
-    const long long q = ((long long)blockIdx.x * kThreads + threadIdx.x) / kG;
-    const bool active = q < BM;
-    const long long qq = active ? q : 0;
-    const int b = (int)(qq / M);
-    if (dw) {
-        if (threadIdx.x < O * C) s_dw[threadIdx.x] = 0.0f;
-        __syncthreads();
-    }
-    float w[O * C];
-#pragma unroll
-    for (int i = 0; i < O * C; ++i) w[i] = weight[i];
-    float x[D], gi[O], di[C];
-#pragma unroll
-    for (int k = 0; k < D; ++k) x[k] = qlocs[qq * D + k];
-#pragma unroll
-    for (int o = 0; o < O; ++o) gi[o] = go[qq * O + o];
-    const float* row = neighbors + qq * K;
-    const float* sl = locs + (size_t)b * N * D;
-    const float* sd = data + (size_t)b * N * C;
-    const float* sg = go + (size_t)b * M * O;  // symmetric mode only (M == N)
-    if (sym) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) di[c] = sd[(qq - (long long)b * M) * C + c];
-    }
-    float a_dq[D], a_dl[D], a_dd[C], a_dw[O * C];
-#pragma unroll
-    for (int k = 0; k < D; ++k) a_dq[k] = a_dl[k] = 0.0f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) a_dd[c] = 0.0f;
-#pragma unroll
-    for (int i = 0; i < O * C; ++i) a_dw[i] = 0.0f;
-
-    for (int jj0 = 0; jj0 < K; jj0 += kG) {
-        const int jj = jj0 + sub;
-        const float nb = (active && jj < K) ? row[jj] : -1.0f;
-        const unsigned neg = __ballot_sync(0xffffffffu, !(nb >= 0.0f));
-        const int fneg = group_first_neg(neg, lane, sub);
-        if (sub < fneg) {
-            const int j = (int)nb;
-            const float* y = sl + (size_t)j * D;
-            float disp[D];
-            float d = 0.0f;
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                disp[k] = x[k] - y[k];
-                d += disp[k] * disp[k];
-            }
-            if (d < rad2) {
-                d = sqrtf(d);
-                float norm = 1.0f;
-                if (dis_norm && d > 0.0f) norm /= d;
-                const bool in = !(d > sp.H);
-                const float kw = in ? sph_eval(sp.w_expr, d, sp.H, sp.w_coef) : 0.0f;
-                const float kdw = (in ? sph_eval(sp.dw_expr, d, sp.H, sp.dw_coef) : 0.0f) / d;
-                float dkw[D];
-#pragma unroll
-                for (int k = 0; k < D; ++k) dkw[k] = kdw * disp[k];
-                float dj[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) dj[c] = sd[(size_t)j * C + c];
-                // ---- this query (row q) as the query of pair (q, j)
-#pragma unroll
-                for (int o = 0; o < O; ++o)
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const float wv = w[o * C + c];
-                        if (dw) a_dw[o * C + c] += gi[o] * dj[c] * kw * norm;
-                        if (d > 0.0f) {
-#pragma unroll
-                            for (int k = 0; k < D; ++k) a_dq[k] += wv * dj[c] * norm * dkw[k] * gi[o];
-                        }
-                    }
-                if (sym) {
-                    // ---- this particle as the NEIGHBOUR of query j (pair (j, q)): same distance,
-                    // displacement negated.  Gathers what the reference scatters with atomics.
-                    float gj[O];
-#pragma unroll
-                    for (int o = 0; o < O; ++o) gj[o] = sg[(size_t)j * O + o];
-#pragma unroll
-                    for (int o = 0; o < O; ++o)
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const float wv = w[o * C + c];
-                            a_dd[c] += gj[o] * wv * kw * norm;
-                            if (d > 0.0f) {
-#pragma unroll
-                                for (int k = 0; k < D; ++k)
-                                    a_dl[k] += -wv * di[c] * norm * (kdw * -disp[k]) * gj[o];
-                            }
-                        }
-                } else {
-                    // ---- scatter onto neighbour j
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        float v = 0.0f;
-#pragma unroll
-                        for (int o = 0; o < O; ++o) v += gi[o] * w[o * C + c] * kw * norm;
-                        if (dd) atomicAdd(dd + ((size_t)b * N + j) * C + c, v);
-                    }
-                    if (dl && d > 0.0f) {
-#pragma unroll
-                        for (int k = 0; k < D; ++k) {
-                            float v = 0.0f;
-#pragma unroll
-                            for (int o = 0; o < O; ++o)
-#pragma unroll
-                                for (int c = 0; c < C; ++c)
-                                    v += -w[o * C + c] * dj[c] * norm * dkw[k] * gi[o];
-                            atomicAdd(dl + ((size_t)b * N + j) * D + k, v);
-                        }
-                    }
-                }
-            }
-        }
-        if (__all_sync(0xffffffffu, fneg < kG)) break;
-    }
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        a_dq[k] = group_sum(a_dq[k]);
-        if (sym) a_dl[k] = group_sum(a_dl[k]);
-    }
-    if (sym) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) a_dd[c] = group_sum(a_dd[c]);
-    }
-    if (active && sub == 0) {
-        if (sym) {
-            if (same_q_l) {
-                if (dq)
-#pragma unroll
-                    for (int k = 0; k < D; ++k) dq[q * D + k] = a_dq[k] + a_dl[k];
-            } else {
-                if (dq)
-#pragma unroll
-                    for (int k = 0; k < D; ++k) dq[q * D + k] = a_dq[k];
-                if (dl)
-#pragma unroll
-                    for (int k = 0; k < D; ++k) dl[q * D + k] = a_dl[k];
-            }
-            if (dd)
-#pragma unroll
-                for (int c = 0; c < C; ++c) dd[q * C + c] = a_dd[c];
-        } else if (dq) {
-            if (same_q_l) {
-#pragma unroll
-                for (int k = 0; k < D; ++k) atomicAdd(dq + q * D + k, a_dq[k]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < D; ++k) dq[q * D + k] = a_dq[k];
-            }
-        }
-    }
-    if (dw) {
-        // warp-reduce, then shared, then one global atomic per weight per block
-#pragma unroll
-        for (int i = 0; i < O * C; ++i) {
-            float v = a_dw[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) atomicAdd(&s_dw[i], v);
-        }
-        __syncthreads();
-        if (threadIdx.x < O * C) atomicAdd(dw + threadIdx.x, s_dw[threadIdx.x]);
-    }
 }
 
 // =================================================================================================
@@ -589,8 +333,6 @@ constexpr int kMaxSmemWeights = 40 * 1024;  // bytes of weights staged per block
 
 using namespace spnb;
 
-#define SPNB_SMALL_CASES(X) X(3, 1, 1) X(3, 3, 3) X(2, 1, 1) X(2, 2, 2)
-
 extern "C" {
 
 int spnb_convsp_forward(const float* qlocs, const float* locs, const float* data,
@@ -609,16 +351,10 @@ int spnb_convsp_forward(const float* qlocs, const float* locs, const float* data
     const long long BM = (long long)B * M;
     const int blocks = cdiv(BM * kG, kThreads);
     bool done = false;
-    if (ncells == 1) {
-#define X(DD, CC, OO)                                                                              \
-    if (!done && D == DD && C == CC && O == OO) {                                                  \
-        k_convsp_fwd_small<DD, CC, OO><<<blocks, kThreads, 0, stream>>>(                           \
-            qlocs, locs, data, neighbors, weight, bias, BM, M, N, K, radius * radius, dis_norm, sp, \
-            out);                                                                                  \
-        done = true;                                                                               \
-    }
-        SPNB_SMALL_CASES(X)
-#undef X
+    if (convsp_small_supported(D, C, O, ncells)) {
+        launch_convsp_fwd_small(qlocs, locs, data, neighbors, weight, bias, B, M, N, C, D, K, O, radius,
+                                dis_norm, kernel_fn, out, stream);
+        done = true;
     }
     if (!done) {
         const size_t wbytes = sizeof(float) * (size_t)O * C * ncells;
@@ -636,6 +372,7 @@ int spnb_convsp_forward(const float* qlocs, const float* locs, const float* data
         }
 #undef LAUNCH
     }
+    count_launches(1);
     return check_launch("spnb_convsp_forward") ? 1 : 0;
 }
 
@@ -671,12 +408,7 @@ int spnb_convsp_backward(const float* qlocs, const float* locs, const float* dat
     if (sym_flag && (qlocs != locs || M != N)) sym_flag = nullptr;
     if (dweight) cudaMemsetAsync(dweight, 0, sizeof(float) * (size_t)O * C * ncells, stream);
 
-    bool small = false;
-    if (ncells == 1) {
-#define X(DD, CC, OO) if (D == DD && C == CC && O == OO) small = true;
-        SPNB_SMALL_CASES(X)
-#undef X
-    }
+    const bool small = convsp_small_supported(D, C, O, ncells);
     // Scatter targets must start from zero whenever the atomic path can run.  (The symmetric
     // gather overwrites, so the fill is redundant there, but whether it runs is only known on the
     // device.)
@@ -684,13 +416,9 @@ int spnb_convsp_backward(const float* qlocs, const float* locs, const float* dat
     if (ddata) cudaMemsetAsync(ddata, 0, sizeof(float) * (size_t)B * N * C, stream);
 
     if (small) {
-#define X(DD, CC, OO)                                                                              \
-    if (D == DD && C == CC && O == OO)                                                             \
-        k_convsp_bwd_small<DD, CC, OO><<<blocks, kThreads, 0, stream>>>(                           \
-            qlocs, locs, data, neighbors, weight, grad_out, BM, M, N, K, radius * radius, dis_norm, \
-            sp, dqlocs, dlocs, ddata, dweight, sym_flag, same);
-        SPNB_SMALL_CASES(X)
-#undef X
+        launch_convsp_bwd_small(qlocs, locs, data, neighbors, weight, B, M, N, C, D, K, O, radius,
+                                dis_norm, kernel_fn, grad_out, dqlocs, dlocs, ddata, dweight, sym_flag,
+                                same, stream);
     } else {
         const size_t wbytes = sizeof(float) * (size_t)O * C * ncells;
         const int ws = 2 * wbytes <= (size_t)(2 * kMaxSmemWeights);
@@ -712,6 +440,7 @@ int spnb_convsp_backward(const float* qlocs, const float* locs, const float* dat
         }
 #undef LAUNCH
     }
+    count_launches(1);
     return check_launch("spnb_convsp_backward") ? 1 : 0;
 }
 

@@ -537,6 +537,7 @@ int spnb_grid_bounds(const float* locs, int B, int N, int D, float radius, int m
     k_bounds_partial<<<dim3(bx, B), 256, 0, stream>>>(locs, acc, N, D);
     k_bounds_final<<<cdiv(B * D, 128), 128, 0, stream>>>(acc, low, grid_dims, B, D, radius,
                                                          (float)max_grid_dim);
+    count_launches(2);
     return check_launch("spnb_grid_bounds") ? 1 : 0;
 }
 
@@ -583,6 +584,7 @@ int spnb_hashgrid_order(const float* locs, const float* low, const float* grid_d
                                                              last ? idxs : nullptr, ctl, hist, status,
                                                              ticket, err, B, N, w.tiles, w.passes, p);
     }
+    count_launches(2 + w.passes);
     return check_launch("spnb_hashgrid_order") ? 1 : 0;
 }
 
@@ -603,6 +605,7 @@ int spnb_reorder_data(const float* locs, const float* data, const float* idxs, f
     int blocks = cdiv(BN * (D + C), 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
     k_reorder<<<blocks, 256, 0, stream>>>(locs, data, idxs, nlocs, ndata, BN, N, D, C, reverse);
+    count_launches(1);
     return check_launch("spnb_reorder_data") ? 1 : 0;
 }
 
@@ -638,6 +641,7 @@ int spnb_compute_collisions(const float* qlocs, const float* locs, const float* 
     default: SPNB_COLLIDE(0); break;
     }
 #undef SPNB_COLLIDE
+    count_launches(3);
     return check_launch("spnb_compute_collisions") ? 1 : 0;
 }
 

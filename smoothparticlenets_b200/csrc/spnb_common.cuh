@@ -15,6 +15,7 @@ namespace spnb {
 
 void set_error(const char* fmt, ...);
 bool check_launch(const char* what);
+void count_launches(int n);  // kernels (not memsets) enqueued by this process, for bench accounting
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
