@@ -7,11 +7,14 @@
 //
 // Design (DESIGN.md "ConvSP list path"):
 //  * a group of 8 lanes owns one query; per step the group reads a 128-byte chunk of the neighbour
-//    row with ONE float4 load per lane (32 entries in flight), so each lane then has 4 independent
-//    gathers (locs / data / grad rows of 4 neighbours) outstanding -- the kernel is latency bound,
-//    and memory-level parallelism per lane is what buys throughput;
+//    row (32 entries in flight: lane `sub` takes entries sub, sub+8, sub+16, sub+24 of the chunk, so
+//    every load instruction of the group covers one 32-byte sector), and each lane then has up to 4
+//    independent gathers (locs / data / grad rows) outstanding -- the kernel is latency bound, and
+//    memory-level parallelism per lane is what buys throughput.  The strided assignment packs a
+//    short tail into slot 0 of the lanes, so the empty slots 1..3 are skipped warp-uniformly;
 //  * the next chunk of the row is requested before the current one is processed, but only once it
 //    is known to be needed (no terminator yet), so short lists cost one 128-byte read;
+//  * blockIdx.y is the scene, so no 64-bit division is needed to find it;
 //  * the in-radius predicate d2 < r*r is evaluated with separately rounded fp32 operations in the
 //    reference's order (this file is compiled with -fmad=false), so membership is bit-identical to
 //    the CPU reference; everything AFTER the predicate (distance, 1/d, W(d), the channel
@@ -31,6 +34,9 @@ constexpr int kG = 8;          // lanes per query
 constexpr int kThreads = 256;  // 32 queries per block
 constexpr int kEPL = 4;        // list entries per lane per chunk (one float4)
 constexpr int kChunk = kG * kEPL;
+#ifndef SPNB_BWD_MIN_BLOCKS
+#define SPNB_BWD_MIN_BLOCKS 3
+#endif
 
 struct SphFast {
     int w_expr, dw_expr;
@@ -66,25 +72,40 @@ __device__ __forceinline__ float sph_fast(int e, float d, float d2, float c, con
     }
 }
 
-__device__ __forceinline__ float4 load_entries(const float* __restrict__ row, int p, int K, bool vec)
+// Entries base+sub, base+sub+8, base+sub+16, base+sub+24 of a row (-1 beyond K).
+__device__ __forceinline__ void load_entries(const float* __restrict__ row, int p, int K, float* e)
 {
-    if (vec && p + 3 < K) return *reinterpret_cast<const float4*>(row + p);
-    float4 v;
-    v.x = p < K ? row[p] : -1.0f;
-    v.y = p + 1 < K ? row[p + 1] : -1.0f;
-    v.z = p + 2 < K ? row[p + 2] : -1.0f;
-    v.w = p + 3 < K ? row[p + 3] : -1.0f;
-    return v;
+    if (p - (p & (kG - 1)) + kChunk <= K) {  // whole chunk inside the row (uniform per group)
+#pragma unroll
+        for (int i = 0; i < kEPL; ++i) e[i] = row[p + i * kG];
+    } else {
+#pragma unroll
+        for (int i = 0; i < kEPL; ++i) e[i] = p + i * kG < K ? row[p + i * kG] : -1.0f;
+    }
 }
 
-// Number of leading non-negative entries of my float4 (the list ends at the first negative one).
-__device__ __forceinline__ int leading_valid(const float4& v)
+// Per-lane number of valid slots in the current chunk and whether the group saw a terminator.
+// The list ends at the first negative entry of the row (common_funcs.h:476).
+__device__ __forceinline__ int chunk_valid(const float* e, int lane, int sub, bool& ended)
 {
-    if (!(v.x >= 0.0f)) return 0;
-    if (!(v.y >= 0.0f)) return 1;
-    if (!(v.z >= 0.0f)) return 2;
-    if (!(v.w >= 0.0f)) return 3;
-    return 4;
+    int first = kChunk;  // position of the first negative entry within the chunk
+#pragma unroll
+    for (int i = kEPL - 1; i >= 0; --i) {
+        const unsigned negb = __ballot_sync(0xffffffffu, !(e[i] >= 0.0f));
+        const unsigned g = (negb >> (lane - sub)) & ((1u << kG) - 1u);
+        if (g) first = i * kG + __ffs(g) - 1;
+    }
+    ended = first < kChunk;
+    // slots i with i*kG + sub < first are valid
+    return first > sub ? (first - sub + kG - 1) / kG : 0;
+}
+
+// 1/sqrt(x) as a single MUFU.RSQ (about 1 ulp); callers guard x > 0.
+__device__ __forceinline__ float fast_rsqrt(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 template <typename T>
@@ -94,14 +115,6 @@ __device__ __forceinline__ T group_sum(T v)
     for (int o = kG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-
-// Walks the neighbour row of one query chunk by chunk; calls body(j) for every valid entry handled
-// by this lane, 4 at a time (body_begin lets the caller issue all gathers before the math).
-struct RowWalk {
-    const float* row;
-    int K, sub, lane;
-    bool vec, active;
-};
 
 // ---- forward -------------------------------------------------------------------------------------
 template <int D, int C, int O, int FN>
@@ -113,10 +126,11 @@ k_convsp_fwd_small(const float* __restrict__ qlocs, const float* __restrict__ lo
                    float* __restrict__ out)
 {
     const int lane = threadIdx.x & 31, sub = lane & (kG - 1);
-    const long long q = ((long long)blockIdx.x * kThreads + threadIdx.x) / kG;
-    const bool active = q < BM;
-    const long long qq = active ? q : 0;
-    const int b = (int)(qq / M);
+    const int b = blockIdx.y;
+    const int m = (blockIdx.x * kThreads + threadIdx.x) / kG;  // query within the scene
+    const bool active = m < M;
+    const long long q = (long long)b * M + m;
+    const long long qq = active ? q : (long long)b * M;
     const int we = FN >= 0 ? FN : sp.w_expr;
     float w[O * C];
 #pragma unroll
@@ -131,48 +145,54 @@ k_convsp_fwd_small(const float* __restrict__ qlocs, const float* __restrict__ lo
 #pragma unroll
     for (int o = 0; o < O; ++o) acc[o] = 0.0f;
 
-    const float4 none = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
-    float4 cur = active ? load_entries(row, sub * kEPL, K, vec) : none;
+    float e[kEPL], nxt[kEPL];
+#pragma unroll
+    for (int i = 0; i < kEPL; ++i) e[i] = nxt[i] = -1.0f;
+    if (active) load_entries(row, sub, K, e);
     for (int base = 0; base < K; base += kChunk) {
-        const int li = leading_valid(cur);
-        const unsigned negb = __ballot_sync(0xffffffffu, li < kEPL);
-        const unsigned g = (negb >> (lane - sub)) & ((1u << kG) - 1u);
-        const int f = g ? __ffs(g) - 1 : kG;  // first lane of my group holding a terminator
-        const int nvalid = sub < f ? kEPL : (sub == f ? li : 0);
-        float4 nxt = none;
-        if (f == kG && base + kChunk < K) nxt = load_entries(row, base + kChunk + sub * kEPL, K, vec);
+        bool ended;
+        const int nvalid = chunk_valid(e, lane, sub, ended);
+        if (!ended && base + kChunk < K) load_entries(row, base + kChunk + sub, K, nxt);
+        const int maxvalid = __reduce_max_sync(0xffffffffu, nvalid);
 
-        const float e[kEPL] = {cur.x, cur.y, cur.z, cur.w};
         float y[kEPL][D], dj[kEPL][C];
 #pragma unroll
         for (int i = 0; i < kEPL; ++i) {
-            const int j = i < nvalid ? (int)e[i] : 0;
+            if (i < maxvalid) {
+                const int j = i < nvalid ? (int)e[i] : 0;
 #pragma unroll
-            for (int k = 0; k < D; ++k) y[i][k] = sl[(size_t)j * D + k];
+                for (int k = 0; k < D; ++k) y[i][k] = sl[(unsigned)j * (unsigned)D + k];
 #pragma unroll
-            for (int c = 0; c < C; ++c) dj[i][c] = sd[(size_t)j * C + c];
+                for (int c = 0; c < C; ++c) dj[i][c] = sd[(unsigned)j * (unsigned)C + c];
+            }
         }
 #pragma unroll
         for (int i = 0; i < kEPL; ++i) {
-            float d2 = 0.0f;
+            if (i < maxvalid) {
+                float d2 = 0.0f;
 #pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const float nr = x[k] - y[i][k];
-                d2 += nr * nr;
-            }
-            if (i < nvalid && d2 < rad2) {
-                const float inv = rsqrtf(d2);
-                const float d = d2 > 0.0f ? d2 * inv : 0.0f;
-                float s = sph_fast(we, d, d2, sp.wc, sp);
-                if (dis_norm && d2 > 0.0f) s *= inv;
+                for (int k = 0; k < D; ++k) {
+                    const float nr = x[k] - y[i][k];
+                    d2 += nr * nr;
+                }
+                if (i < nvalid && d2 < rad2) {
+                    const float inv = fast_rsqrt(d2);
+                    const float d = d2 > 0.0f ? d2 * inv : 0.0f;
+                    float s = sph_fast(we, d, d2, sp.wc, sp);
+                    if (dis_norm && d2 > 0.0f) s *= inv;
 #pragma unroll
-                for (int o = 0; o < O; ++o)
+                    for (int o = 0; o < O; ++o)
 #pragma unroll
-                    for (int c = 0; c < C; ++c) acc[o] = fmaf(w[o * C + c] * dj[i][c], s, acc[o]);
+                        for (int c = 0; c < C; ++c) acc[o] = fmaf(w[o * C + c] * dj[i][c], s, acc[o]);
+                }
             }
         }
-        if (__all_sync(0xffffffffu, f < kG)) break;
-        cur = nxt;
+        if (__all_sync(0xffffffffu, ended)) break;
+#pragma unroll
+        for (int i = 0; i < kEPL; ++i) {
+            e[i] = nxt[i];
+            nxt[i] = -1.0f;
+        }
     }
 #pragma unroll
     for (int o = 0; o < O; ++o) acc[o] = group_sum(acc[o]);
@@ -185,7 +205,7 @@ k_convsp_fwd_small(const float* __restrict__ qlocs, const float* __restrict__ lo
 // ---- backward ------------------------------------------------------------------------------------
 // `go` = grad_output [B,M,O].  See spnb_convsp_backward (include/spnb.h) for the buffer contract.
 template <int D, int C, int O, int FN, bool WDW>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, SPNB_BWD_MIN_BLOCKS)
 k_convsp_bwd_small(const float* __restrict__ qlocs, const float* __restrict__ locs,
                    const float* __restrict__ data, const float* __restrict__ neighbors,
                    const float* __restrict__ weight, const float* __restrict__ go, long long BM,
@@ -195,10 +215,11 @@ k_convsp_bwd_small(const float* __restrict__ qlocs, const float* __restrict__ lo
     __shared__ float s_dw[WDW ? O * C : 1];
     const bool sym = sym_flag != nullptr && *sym_flag == 0;
     const int lane = threadIdx.x & 31, sub = lane & (kG - 1);
-    const long long q = ((long long)blockIdx.x * kThreads + threadIdx.x) / kG;
-    const bool active = q < BM;
-    const long long qq = active ? q : 0;
-    const int b = (int)(qq / M);
+    const int b = blockIdx.y;
+    const int m = (blockIdx.x * kThreads + threadIdx.x) / kG;  // query within the scene
+    const bool active = m < M;
+    const long long q = (long long)b * M + m;
+    const long long qq = active ? q : (long long)b * M;
     const int we = FN >= 0 ? FN : sp.w_expr;
     const int dwe = FN >= 0 ? (FN == E_SPIKY ? E_DSPIKY : FN == E_DSPIKY ? E_D_DSPIKY
                               : FN == E_CONSTANT ? E_D_CONSTANT : FN == E_COHESION ? E_D_COHESION
@@ -229,35 +250,35 @@ k_convsp_bwd_small(const float* __restrict__ qlocs, const float* __restrict__ lo
 #pragma unroll
     for (int i = 0; i < (WDW ? O * C : 1); ++i) a_dw[i] = 0.0f;
 
-    const float4 none = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
-    float4 cur = active ? load_entries(row, sub * kEPL, K, vec) : none;
+    float e[kEPL], nxt[kEPL];
+#pragma unroll
+    for (int i = 0; i < kEPL; ++i) e[i] = nxt[i] = -1.0f;
+    if (active) load_entries(row, sub, K, e);
     for (int base = 0; base < K; base += kChunk) {
-        const int li = leading_valid(cur);
-        const unsigned negb = __ballot_sync(0xffffffffu, li < kEPL);
-        const unsigned g = (negb >> (lane - sub)) & ((1u << kG) - 1u);
-        const int f = g ? __ffs(g) - 1 : kG;
-        const int nvalid = sub < f ? kEPL : (sub == f ? li : 0);
-        float4 nxt = none;
-        if (f == kG && base + kChunk < K) nxt = load_entries(row, base + kChunk + sub * kEPL, K, vec);
+        bool ended;
+        const int nvalid = chunk_valid(e, lane, sub, ended);
+        if (!ended && base + kChunk < K) load_entries(row, base + kChunk + sub, K, nxt);
+        const int maxvalid = __reduce_max_sync(0xffffffffu, nvalid);
 
-        const float e[kEPL] = {cur.x, cur.y, cur.z, cur.w};
         int jn[kEPL];
         float y[kEPL][D], dj[kEPL][C], gj[kEPL][O];
 #pragma unroll
         for (int i = 0; i < kEPL; ++i) {
+            if (i >= maxvalid) continue;
             const int j = i < nvalid ? (int)e[i] : 0;
             jn[i] = j;
 #pragma unroll
-            for (int k = 0; k < D; ++k) y[i][k] = sl[(size_t)j * D + k];
+            for (int k = 0; k < D; ++k) y[i][k] = sl[(unsigned)j * (unsigned)D + k];
 #pragma unroll
-            for (int c = 0; c < C; ++c) dj[i][c] = sd[(size_t)j * C + c];
+            for (int c = 0; c < C; ++c) dj[i][c] = sd[(unsigned)j * (unsigned)C + c];
             if (sym) {
 #pragma unroll
-                for (int o = 0; o < O; ++o) gj[i][o] = sg[(size_t)j * O + o];
+                for (int o = 0; o < O; ++o) gj[i][o] = sg[(unsigned)j * (unsigned)O + o];
             }
         }
 #pragma unroll
         for (int i = 0; i < kEPL; ++i) {
+            if (i >= maxvalid) continue;
             float disp[D];
             float d2 = 0.0f;
 #pragma unroll
@@ -266,7 +287,7 @@ k_convsp_bwd_small(const float* __restrict__ qlocs, const float* __restrict__ lo
                 d2 += disp[k] * disp[k];
             }
             if (i < nvalid && d2 < rad2) {
-                const float inv = rsqrtf(d2);
+                const float inv = fast_rsqrt(d2);
                 const bool pos = d2 > 0.0f;
                 const float d = pos ? d2 * inv : 0.0f;
                 const float norm = (dis_norm && pos) ? inv : 1.0f;
@@ -319,13 +340,25 @@ k_convsp_bwd_small(const float* __restrict__ qlocs, const float* __restrict__ lo
                 }
             }
         }
-        if (__all_sync(0xffffffffu, f < kG)) break;
-        cur = nxt;
+        if (__all_sync(0xffffffffu, ended)) break;
+#pragma unroll
+        for (int i = 0; i < kEPL; ++i) {
+            e[i] = nxt[i];
+            nxt[i] = -1.0f;
+        }
+    }
+    if (sym && same_q_l) {
+        // only the sum d/dqlocs + d/dlocs is wanted: reduce once
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            a_dq[k] += a_dl[k];
+            a_dl[k] = 0.0f;
+        }
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         a_dq[k] = group_sum(a_dq[k]);
-        if (sym) a_dl[k] = group_sum(a_dl[k]);
+        if (sym && !same_q_l) a_dl[k] = group_sum(a_dl[k]);
     }
     if (sym) {
 #pragma unroll
@@ -415,7 +448,7 @@ void launch_convsp_fwd_small(const float* qlocs, const float* locs, const float*
 {
     const SphFast sp = make_fast(make_sph_params(kernel_fn, radius));
     const long long BM = (long long)B * M;
-    const int blocks = cdiv(BM * kG, kThreads);
+    const dim3 blocks(cdiv((long long)M * kG, kThreads), B);
     const int vec = rows_vectorizable(neighbors, K) ? 1 : 0;
     const float rad2 = radius * radius;
     bool done = false;
@@ -443,7 +476,7 @@ void launch_convsp_bwd_small(const float* qlocs, const float* locs, const float*
 {
     const SphFast sp = make_fast(make_sph_params(kernel_fn, radius));
     const long long BM = (long long)B * M;
-    const int blocks = cdiv(BM * kG, kThreads);
+    const dim3 blocks(cdiv((long long)M * kG, kThreads), B);
     const int vec = rows_vectorizable(neighbors, K) ? 1 : 0;
     const float rad2 = radius * radius;
     bool done = false;

@@ -15,9 +15,9 @@
 //    obtains its global offsets by decoupled look-back over single-word {flag,count} statuses, and
 //    scatters.  Tiles take tickets from an atomic counter so every predecessor is already running.
 //    Only ceil(log2(ncells+1)) key bits are sorted, split evenly over the passes on the device;
-//  * neighbour lists: one warp per query; the 3^D cells are scanned as ONE concatenated candidate
-//    range (warp prefix sum + per-lane search), hits are compacted with ballot/popc so rows are
-//    written coalesced, including the -1 padding.
+//  * neighbour lists: one warp per 8 consecutive queries; queries in the same cell share a candidate
+//    set that is resolved once and staged in shared memory, hits are compacted with ballot/popc so
+//    rows are written coalesced, including the -1 padding.
 #include "spnb_common.cuh"
 
 namespace spnb {
@@ -387,103 +387,162 @@ k_table_fill(const uint32_t* __restrict__ keys, const float* __restrict__ grid_d
 }
 
 // ---- neighbour lists -----------------------------------------------------------------------------
-// One warp per query.  Cells are visited in the reference's odometer order over {-1,0,1}^D with
-// dimension 0 fastest (common_funcs.h:906,938-943); inside a cell candidates come in sorted order.
+// One warp per kQPW consecutive queries.  Consecutive queries that fall in the same grid cell (all of
+// them, when the queries are the cell-sorted particles themselves) share one candidate set: the
+// 3^D neighbour cells are resolved ONCE per run (cell table lookups, warp prefix sum), the
+// candidates' indices and coordinates are staged in shared memory, and every query of the run then
+// streams over the staged candidates 32 at a time -- distance test, ballot/popc compaction,
+// coalesced row writes, -1 padding.  Cells are visited in the reference's odometer order over
+// {-1,0,1}^D with dimension 0 fastest and candidates inside a cell in sorted order
+// (common_funcs.h:906-943), so rows are bit-identical to the reference's, truncation included.
+constexpr int kQPW = 8;          // queries per warp
+constexpr int kCollideWarps = 8;  // warps per block
+
 template <int DT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kCollideWarps * 32)
 k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
           const float* __restrict__ low, const float* __restrict__ grid_dims,
           const float* __restrict__ starts, const float* __restrict__ ends,
-          float* __restrict__ coll, int B, int M, int N, int ndims, int K, int ncells, float edge,
-          float r2, int include_self, int* trunc_flag)
+          float* __restrict__ coll, int M, int N, int ndims, int K, int ncells, float edge, float r2,
+          int include_self, int* trunc_flag)
 {
+    constexpr int MD = DT > 0 ? DT : SPNB_MAXD;
+    constexpr int CM = DT > 0 ? 256 : 64;  // staged candidates per window
     const int D = DT > 0 ? DT : ndims;
-    constexpr int kWarps = 8;
-    __shared__ int s_off[kWarps][33];
-    __shared__ int s_start[kWarps][32];
+    __shared__ int s_off[kCollideWarps][33];
+    __shared__ int s_start[kCollideWarps][32];
+    __shared__ int s_idx[kCollideWarps][CM];
+    __shared__ float s_y[kCollideWarps][MD][CM];
+    __shared__ int s_found[kCollideWarps][kQPW];
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long q = (long long)blockIdx.x * kWarps + warp;
-    if (q >= (long long)B * M) return;
-    const int b = (int)(q / M);
-    const float* x = qlocs + q * D;
+    const int b = blockIdx.y;
+    const int q0 = (blockIdx.x * kCollideWarps + warp) * kQPW;
+    if (q0 >= M) return;
+    const int nq = min(kQPW, M - q0);
     const float* gd = grid_dims + b * D;
-    float xq[DT > 0 ? DT : SPNB_MAXD];
-    int gc[DT > 0 ? DT : SPNB_MAXD];
+    const float* lo = low + b * D;
+    const float* sl = locs + (size_t)b * N * D;
+    const float* sq = qlocs + ((size_t)b * M + q0) * D;
+    float* rows = coll + ((size_t)b * M + q0) * K;
+    const float* st = starts + (size_t)b * ncells;
+    const float* en = ends + (size_t)b * ncells;
     int total_cells = 1;
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        xq[k] = x[k];
-        gc[k] = grid_coord_of(xq[k], low[b * D + k], edge);
-        total_cells *= 3;
-    }
-    float* row = coll + q * K;
-    const float* sl = locs + (size_t)b * N * D;
-    int found = 0;
+    for (int k = 0; k < D; ++k) total_cells *= 3;
+    bool truncated = false;
 
-    for (int cell0 = 0; cell0 < total_cells && found < K; cell0 += 32) {
-        // lane -> one neighbour cell of this chunk
-        const int ci = cell0 + lane;
-        int cnt = 0, cstart = 0;
-        if (ci < total_cells) {
-            int rem = ci, id = 0;
-            bool ok = true;
+    int qi = 0;
+    while (qi < nq) {
+        // ---- the run of queries sharing the cell of query qi
+        int gc[MD];
 #pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const int c = gc[k] + (rem % 3) - 1;
-                rem /= 3;
-                if (c < 0 || (float)c >= gd[k]) ok = false;
-                else id += hash_term(c, gd, k, D);
-            }
-            if (ok && id >= 0 && id < ncells) {
-                cstart = (int)starts[(size_t)b * ncells + id];
-                cnt = (int)ends[(size_t)b * ncells + id] - cstart;
-                if (cnt < 0) cnt = 0;
-            }
-        }
-        int incl = cnt;
+        for (int k = 0; k < D; ++k) gc[k] = grid_coord_of(sq[qi * D + k], lo[k], edge);
+        bool same = lane < nq - qi;
+        if (same) {
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
+            for (int k = 0; k < D; ++k)
+                same = same && grid_coord_of(sq[(qi + lane) * D + k], lo[k], edge) == gc[k];
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        __syncwarp();
-        s_off[warp][lane + 1] = incl;
-        if (lane == 0) s_off[warp][0] = 0;
-        s_start[warp][lane] = cstart;
+        const unsigned sm = __ballot_sync(0xffffffffu, same);
+        const int run = __ffs(~sm) - 1;  // leading ones (lane 0 always matches itself)
+        if (lane < run) s_found[warp][lane] = 0;
         __syncwarp();
 
-        for (int base = 0; base < total && found < K; base += 32) {
-            const int t = base + lane;
-            bool hit = false;
-            int idx = 0;
-            if (t < total) {
-                // largest c with s_off[c] <= t  (5-step binary search over 32 entries)
-                int c = 0;
-#pragma unroll
-                for (int s = 16; s > 0; s >>= 1)
-                    if (s_off[warp][c + s] <= t) c += s;
-                idx = s_start[warp][c] + (t - s_off[warp][c]);
-                const float* y = sl + (size_t)idx * D;
-                float d = 0.0f;
+        for (int cell0 = 0; cell0 < total_cells; cell0 += 32) {
+            // ---- lane -> one neighbour cell of this chunk: range of sorted particles in it
+            const int ci = cell0 + lane;
+            int cnt = 0, cstart = 0;
+            if (ci < total_cells) {
+                int rem = ci, id = 0;
+                bool ok = true;
 #pragma unroll
                 for (int k = 0; k < D; ++k) {
-                    const float nr = xq[k] - y[k];
-                    d += nr * nr;
+                    const int c = gc[k] + (rem % 3) - 1;
+                    rem /= 3;
+                    if (c < 0 || (float)c >= gd[k]) ok = false;
+                    else id += hash_term(c, gd, k, D);
                 }
-                hit = d < r2 && (d > 0.0f || include_self);
+                if (ok && id >= 0 && id < ncells) {
+                    cstart = (int)st[id];
+                    cnt = (int)en[id] - cstart;
+                    if (cnt < 0) cnt = 0;
+                }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            const int pos = found + __popc(m & lanemask_lt());
-            if (hit && pos < K) row[pos] = (float)idx;
-            found += __popc(m);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            s_off[warp][lane + 1] = incl;
+            if (lane == 0) s_off[warp][0] = 0;
+            s_start[warp][lane] = cstart;
+            __syncwarp();
+
+            for (int w0 = 0; w0 < total; w0 += CM) {
+                // ---- stage a window of candidates: index + coordinates
+                const int wn = min(CM, total - w0);
+                for (int t = lane; t < wn; t += 32) {
+                    const int tt = w0 + t;
+                    int c = 0;  // largest c with s_off[c] <= tt
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1)
+                        if (s_off[warp][c + s] <= tt) c += s;
+                    const int idx = s_start[warp][c] + (tt - s_off[warp][c]);
+                    s_idx[warp][t] = idx;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) s_y[warp][k][t] = sl[(size_t)idx * D + k];
+                }
+                __syncwarp();
+                // ---- every query of the run scans the window
+                for (int r = 0; r < run; ++r) {
+                    int found = s_found[warp][r];
+                    if (found >= K) continue;
+                    float x[MD];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) x[k] = sq[(qi + r) * D + k];
+                    float* row = rows + (size_t)(qi + r) * K;
+                    for (int base = 0; base < wn && found < K; base += 32) {
+                        const int t = base + lane;
+                        bool hit = false;
+                        int idx = 0;
+                        if (t < wn) {
+                            float d = 0.0f;
+#pragma unroll
+                            for (int k = 0; k < D; ++k) {
+                                const float nr = x[k] - s_y[warp][k][t];
+                                d += nr * nr;
+                            }
+                            hit = d < r2 && (d > 0.0f || include_self);
+                            idx = s_idx[warp][t];
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, hit);
+                        const int pos = found + __popc(m & lanemask_lt());
+                        if (hit && pos < K) row[pos] = (float)idx;
+                        found += __popc(m);
+                    }
+                    if (lane == 0) s_found[warp][r] = found;
+                }
+                __syncwarp();
+            }
         }
+        // ---- terminate / pad the rows of the run
+        for (int r = 0; r < run; ++r) {
+            int found = s_found[warp][r];
+            if (found >= K) {
+                truncated = true;
+                found = K;
+            }
+            float* row = rows + (size_t)(qi + r) * K;
+            for (int p = found + lane; p < K; p += 32) row[p] = -1.0f;
+        }
+        __syncwarp();
+        qi += run;
     }
-    if (found >= K) {
-        if (trunc_flag && lane == 0) atomicOr(trunc_flag, 1);
-        found = K;
-    }
-    for (int p = found + lane; p < K; p += 32) row[p] = -1.0f;
+    if (truncated && trunc_flag && lane == 0) atomicOr(trunc_flag, 1);
 }
 
 // ---- launch helpers --------------------------------------------------------------------------------
@@ -629,11 +688,11 @@ int spnb_compute_collisions(const float* qlocs, const float* locs, const float* 
     k_table_fill<<<dim3(cdiv(N, 256), B), 256, 0, stream>>>((const uint32_t*)cellIDs, grid_dims,
                                                             cellStarts, cellEnds, N, D, ncells);
     const float r2 = radius * radius;
-    const int blocks = cdiv((long long)B * M, 8);
+    const dim3 blocks(cdiv(M, kCollideWarps * kQPW), B);
 #define SPNB_COLLIDE(DT)                                                                          \
-    k_collide<DT><<<blocks, 256, 0, stream>>>(qlocs, locs, low, grid_dims, cellStarts, cellEnds,   \
-                                              collisions, B, M, N, D, K, ncells, cellEdge, r2,     \
-                                              include_self, trunc_flag)
+    k_collide<DT><<<blocks, kCollideWarps * 32, 0, stream>>>(                                      \
+        qlocs, locs, low, grid_dims, cellStarts, cellEnds, collisions, M, N, D, K, ncells, cellEdge, \
+        r2, include_self, trunc_flag)
     switch (D) {
     case 1: SPNB_COLLIDE(1); break;
     case 2: SPNB_COLLIDE(2); break;

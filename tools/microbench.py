@@ -1,0 +1,118 @@
+"""Micro-benchmark of individual libspnb launches on the c2 workload (8 x 65536 particles).
+
+    python tools/microbench.py [--only fwd1,fwd3,bwd1,bwd3,collide,sort,reorder] [--iters 20]
+
+Prints ms per launch, algorithmic GB/s (SURVEY.md 8(d) byte counts) and fraction of the measured HBM
+peak.  Meant to be wrapped in ncu for a single kernel:
+    ncu --set full --clock-control none --import-source on -k regex:k_convsp_fwd_small -s 5 -c 1 \
+        -o gpurun_out/prof python tools/microbench.py --only fwd1 --iters 3
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+import cases  # noqa: E402
+import fluidstep  # noqa: E402
+import smoothparticlenets_b200 as spn  # noqa: E402
+from smoothparticlenets_b200 import _native as nat  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="fwd1,fwd3,bwd1,bwd3,collide,search,reorder")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--scenes", type=int, default=8)
+    ap.add_argument("--particles", type=int, default=65536)
+    ap.add_argument("--kernel", default="dspiky")
+    ap.add_argument("--nosym", action="store_true")
+    args = ap.parse_args()
+    only = set(args.only.split(","))
+    B, N, D, R, K = args.scenes, args.particles, 3, 0.1, 128
+    locs_h, vel_h, _ = cases.fluid_cloud(1000, B, N)
+    locs, vel = torch.from_numpy(locs_h).cuda(), torch.from_numpy(vel_h).cuda()
+    model = fluidstep.FluidStep(spn, radius=R, max_collisions=K).cuda()
+    L = nat.lib()
+    with torch.no_grad():
+        sl, sv, idxs, nb = model.coll(locs, vel)
+    nbar = float((nb >= 0).sum().item()) / (B * N)
+    flag = None if args.nosym else nb._spnb_sym_flag
+    peak = 6550.1
+    pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pp):
+        peak = json.load(open(pp))["hbm_gbs"]
+    st = nat.stream()
+    ones = torch.ones(B, N, 1, device="cuda")
+    go1, go3 = torch.rand(B, N, 1, device="cuda"), torch.rand(B, N, 3, device="cuda")
+    l1 = getattr(model, args.kernel + "1" + ("normd" if args.kernel in ("dspiky", "cohesion") else ""))
+    l3 = getattr(model, args.kernel + "D" + ("normd" if args.kernel in ("dspiky", "cohesion") else ""))
+
+    def fwd(layer, data, O):
+        out = torch.empty(B, N, O, device="cuda")
+        return lambda: L.spnb_convsp_forward(
+            nat.ptr(sl), nat.ptr(sl), nat.ptr(data), nat.ptr(nb), nat.ptr(layer.weight), nat.ptr(layer.bias),
+            B, N, N, data.shape[2], D, K, O, 1, R, nat.ptr(layer.kernel_size), nat.ptr(layer.dilation),
+            layer.dis_norm, layer.kernel_fn, nat.ptr(out), st)
+
+    def bwd(layer, data, go):
+        dl, dd = torch.empty_like(sl), torch.empty_like(data)
+        return lambda: L.spnb_convsp_backward(
+            nat.ptr(sl), nat.ptr(sl), nat.ptr(data), nat.ptr(nb), nat.ptr(layer.weight), B, N, N,
+            data.shape[2], D, K, go.shape[2], 1, R, nat.ptr(layer.kernel_size), nat.ptr(layer.dilation),
+            layer.dis_norm, layer.kernel_fn, nat.ptr(go), nat.ptr(dl), nat.ptr(dl), nat.ptr(dd), None,
+            nat.ptr(flag), None, st)
+
+    def search():
+        with torch.no_grad():
+            model.coll(locs, vel)
+
+    low, gd = model.coll.last_lower_bounds, model.coll.last_grid_dims
+    coll_out = torch.empty_like(nb)
+    tflag = torch.zeros(1, device="cuda", dtype=torch.int32)
+
+    def collide():
+        L.spnb_compute_collisions(nat.ptr(sl), nat.ptr(sl), nat.ptr(low), nat.ptr(gd), nat.ptr(model.coll.cellIDs),
+                                  nat.ptr(model.coll.cellStarts), nat.ptr(model.coll.cellEnds), nat.ptr(coll_out),
+                                  B, N, N, D, K, 96 ** 3, R, R, 0, nat.ptr(tflag), st)
+
+    ro_l, ro_v = torch.empty_like(locs), torch.empty_like(vel)
+
+    def reorder():
+        L.spnb_reorder_data(nat.ptr(locs), nat.ptr(vel), nat.ptr(idxs), nat.ptr(ro_l), nat.ptr(ro_v), B, N, D, 3, 0, st)
+
+    P = B * N
+    fb = lambda C, O: 4 * D + 4 * C + 4 * (nbar + 1) + 4 * O
+    bb = lambda C, O: fb(C, O) + 8 * D + 4 * C
+    table = {
+        "fwd1": (fwd(l1, ones, 1), P * fb(1, 1)), "fwd3": (fwd(l3, sl, 3), P * fb(3, 3)),
+        "bwd1": (bwd(l1, ones, go1), P * bb(1, 1)), "bwd3": (bwd(l3, sl, go3), P * bb(3, 3)),
+        "collide": (collide, P * (4 * D + 4 + 4 * K)),
+        "search": (search, P * (12 + 20 + 52 + 528)),
+        "reorder": (reorder, P * 52),
+    }
+    print("nbar %.2f  peak %.0f GB/s" % (nbar, peak))
+    for name, (fn, byts) in table.items():
+        if name not in only:
+            continue
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.iters
+        gbs = byts / (ms * 1e-3) / 1e9
+        print("%-8s %8.4f ms  %8.1f GB/s algorithmic  %.3f of peak" % (name, ms, gbs, gbs / peak))
+
+
+if __name__ == "__main__":
+    main()
