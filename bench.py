@@ -241,7 +241,7 @@ def run_ours(args):
     locs_pin = torch.from_numpy(locs_h).pin_memory()
     vel_pin = torch.from_numpy(vel_h).pin_memory()
     locs, vel = locs_pin.cuda(), vel_pin.cuda()
-    model = fluidstep.FluidStep(spn, radius=RADIUS, max_collisions=K_NEIGH).cuda()
+    model = fluidstep.FluidStep(spn, radius=RADIUS, max_collisions=K_NEIGH, fused=args.fused).cuda()
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
     grad_outs = [torch.rand(B, N, 3, device="cuda", generator=g) for _ in range(2)]
 
@@ -337,6 +337,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(B, N), "scenes_per_gpu": B, "particles_per_scene": N,
                        "nbar": round(nbar, 2), "execution": "one CUDA graph per fwd+bwd step",
+                       "convsp_path": "ConvSPGroup (fused per dependency phase)" if args.fused else "per-layer drop-in modules",
                        "l2": "inputs larger than L2 (neighbour lists alone are %d MB per GPU)" % (B * N * K_NEIGH * 4 >> 20),
                        "outputs_finite": finite},
             "clocks": clk,
@@ -372,6 +373,8 @@ def main():
     ap.add_argument("--particles", type=int, default=PARTICLES)
     ap.add_argument("--cpu-particles", type=int, default=CPU_SAMPLE_PARTICLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused", action="store_true",
+                    help="evaluate layers that share (locs, neighbors) through ConvSPGroup (opt-in extension)")
     args = ap.parse_args()
     if args.impl == "reference":
         # bounded sample: each step is one 8192-particle scene per host core (~2.5 s)

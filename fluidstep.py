@@ -65,9 +65,13 @@ def rest_density(kernel_fn, radius):
 
 
 class FluidStep(nn.Module):
-    def __init__(self, ns, radius=0.1, ndim=3, max_collisions=128, kernel_fn_table=None):
+    def __init__(self, ns, radius=0.1, ndim=3, max_collisions=128, kernel_fn_table=None, fused=False):
+        """fused=True evaluates the layers that share (locs, neighbors) through ns.ConvSPGroup (one walk
+        over the neighbour lists per dependency phase) instead of one call per layer; results are the
+        same within fp32 rounding."""
         super(FluidStep, self).__init__()
         self.radius, self.ndim = radius, ndim
+        self.fused = bool(fused)
         kf = kernel_fn_table if kernel_fn_table is not None else ns.KERNEL_FN
         self.density_rest, self.stiffness = rest_density(kf, radius)
         self.max_speed = 0.5 * 0.1 / DT
@@ -85,6 +89,12 @@ class FluidStep(nn.Module):
             setattr(self, "%s%s%s" % (kernel, "D" if dim == 'D' else "1", "normd" if normed else ""), conv)
         self.register_buffer("gravity", torch.tensor(GRAVITY[:ndim], dtype=torch.float32).view(1, 1, -1))
         self.relu = nn.ReLU()
+        if self.fused:
+            self.group_a = ns.ConvSPGroup([self.spiky1, self.dspikyDnormd, self.dspiky1normd,
+                                           self.cohesionDnormd, self.cohesion1normd, self.constant1])
+            self.group_b = ns.ConvSPGroup([self.dspikyDnormd, self.dspiky1normd])
+            self.group_c = ns.ConvSPGroup([self.constantD])
+            self.group_v = ns.ConvSPGroup([self.spikyD, self.spiky1])
 
     def _cap_magnitude(self, A, cap):  # fluid_sim.py:240-245
         vv = torch.norm(A, 2, A.dim() - 1, keepdim=True)
@@ -99,7 +109,25 @@ class FluidStep(nn.Module):
         vel = self._cap_magnitude(vel, self.max_speed)
         new_locs = locs + vel * dt
         new_locs, vel, pidxs, neighbors = self.coll(new_locs, vel)
-        for _ in range(NUM_ITERATIONS):
+        for _ in range(NUM_ITERATIONS if self.fused else 0):
+            # same data flow as below; layers sharing (new_locs, neighbors) grouped by dependency
+            density, nj, ni_s, nj_c, ni_cs, ncount = self.group_a(
+                new_locs, [ones, new_locs, ones, new_locs, ones, ones], neighbors)
+            nij = new_locs * ni_s - nj
+            pressure = self.stiffness * self.relu(density - self.density_rest)
+            njp, nip_s = self.group_b(new_locs, [new_locs * pressure, pressure], neighbors)
+            nijp = new_locs * nip_s - njp
+            delta = -(pressure * nij + nijp)
+            nij = new_locs * ni_cs - nj_c
+            delta = delta + -COHESION * nij * self.radius
+            normals = nij * SURFACE_TENSION / self.density_rest / SURFACE_CONSTRAINT_SCALE
+            cd, = self.group_c(new_locs, [normals], neighbors)
+            delta = delta + (cd - normals * ncount)
+            scale = ncount / (1.0 + RELAXATION)
+            scale = self.relu(scale - DAMP) + DAMP
+            delta = delta / scale
+            new_locs = new_locs + delta
+        for _ in range(0 if self.fused else NUM_ITERATIONS):
             density = self.spiky1(new_locs, ones, neighbors)
             nj = self.dspikyDnormd(new_locs, new_locs, neighbors)
             ni = new_locs * self.dspiky1normd(new_locs, ones, neighbors)
@@ -121,8 +149,12 @@ class FluidStep(nn.Module):
             delta = delta / scale
             new_locs = new_locs + delta
         vel = (new_locs - self.reorder_un2sort(pidxs, locs)) / dt
-        vj = self.spikyD(new_locs, vel, neighbors)
-        vi = vel * self.spiky1(new_locs, ones, neighbors)
+        if self.fused:
+            vj, vi_s = self.group_v(new_locs, [vel, ones], neighbors)
+            vi = vel * vi_s
+        else:
+            vj = self.spikyD(new_locs, vel, neighbors)
+            vi = vel * self.spiky1(new_locs, ones, neighbors)
         vel = vel + dt * VISCOSITY / self.density_rest * (vj - vi)
         new_locs, vel = self.reorder_sort2un(pidxs, new_locs, vel)
         return new_locs, vel

@@ -111,6 +111,35 @@ int spnb_convsp_backward(const float* qlocs, const float* locs, const float* dat
                          float* ddata, float* dweight, const int* sym_flag, void* workspace,
                          void* stream);
 
+/* ---- fused ConvSP group (no reference counterpart) ------------------------ */
+
+/* Several ConvSP layers with kernel_size 1 that share (locs, neighbors, radius) and use the particles
+ * as their own queries (qlocs == locs), evaluated in one walk over the neighbour lists.  Per layer the
+ * result is identical to spnb_convsp_forward / spnb_convsp_backward (within fp32 rounding).  Only a
+ * fixed set of channel layouts is compiled in; for any other layout the functions return 0 /
+ * workspace size 0 ("unsupported group signature") and the caller uses the per-layer entry points. */
+typedef struct SpnbGroupLayer {
+    const float* data;     /* [B,N,nchannels]; may be the locs pointer itself */
+    const float* weight;   /* [nkernels,nchannels,1] */
+    const float* bias;     /* [nkernels] or NULL (forward) */
+    float* out;            /* forward: [B,N,nkernels] */
+    const float* grad_out; /* backward: [B,N,nkernels] */
+    float* ddata;          /* backward: [B,N,nchannels] or NULL */
+    int nchannels, nkernels, kernel_fn, dis_norm;
+} SpnbGroupLayer;
+
+size_t spnb_convsp_group_workspace_bytes(const float* locs, int batch_size, int N, int ndims, float radius,
+                                         int nlayers, const SpnbGroupLayer* layers, int backward);
+int spnb_convsp_group_forward(const float* locs, const float* neighbors, int batch_size, int N, int ndims,
+                              int max_neighbors, float radius, int nlayers, const SpnbGroupLayer* layers,
+                              void* workspace, size_t workspace_bytes, void* stream);
+/* dlocs [B,N,ndims] receives d/dlocs through the geometry of ALL layers (query + neighbour roles);
+ * gradients that reach locs through a data tensor aliasing it are in that layer's ddata. */
+int spnb_convsp_group_backward(const float* locs, const float* neighbors, int batch_size, int N, int ndims,
+                               int max_neighbors, float radius, int nlayers, const SpnbGroupLayer* layers,
+                               float* dlocs, const int* sym_flag, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
 /* ---- ConvSDF ---------------------------------------------------------------------------------- */
 
 /* Forward (bias added in the kernel, as common_funcs.h:834-835).  Replaces cuda_convsdf with NULL

@@ -12,9 +12,10 @@ __init__.py:5-10).  Native code: libspnb.so (C ABI in include/spnb.h), built by
 """
 from .kernels import KERNEL_NAMES, KERNEL_FN, DKERNEL_FN, KERNELS, DKERNELS  # noqa: F401
 from .convsp import ConvSP  # noqa: F401
+from .convsp_group import ConvSPGroup  # noqa: F401
 from .particlecollision import ParticleCollision, ReorderData  # noqa: F401
 from .convsdf import ConvSDF  # noqa: F401
 from . import error_checking  # noqa: F401
 
-__all__ = ["ConvSP", "ConvSDF", "ParticleCollision", "ReorderData", "KERNEL_NAMES", "KERNEL_FN",
+__all__ = ["ConvSP", "ConvSPGroup", "ConvSDF", "ParticleCollision", "ReorderData", "KERNEL_NAMES", "KERNEL_FN",
            "DKERNEL_FN", "KERNELS", "DKERNELS"]

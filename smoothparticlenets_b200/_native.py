@@ -27,6 +27,9 @@ _SIGNATURES = {
     "spnb_convsp_forward": (_i, [_vp] * 6 + [_i] * 8 + [_f, _vp, _vp, _i, _i, _vp, _vp]),
     "spnb_convsp_backward_workspace_bytes": (_sz, [_i, _i, _i]),
     "spnb_convsp_backward": (_i, [_vp] * 5 + [_i] * 8 + [_f, _vp, _vp, _i, _i] + [_vp] * 8),
+    "spnb_convsp_group_workspace_bytes": (_sz, [_vp, _i, _i, _i, _f, _i, _vp, _i]),
+    "spnb_convsp_group_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _sz, _vp]),
+    "spnb_convsp_group_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "spnb_convsdf_forward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp, _i, _vp,
                                   _vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "spnb_convsdf_backward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp, _i, _vp,
@@ -34,6 +37,12 @@ _SIGNATURES = {
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class GroupLayer(ctypes.Structure):
+    """struct SpnbGroupLayer (include/spnb.h)."""
+    _fields_ = [("data", _vp), ("weight", _vp), ("bias", _vp), ("out", _vp), ("grad_out", _vp),
+                ("ddata", _vp), ("nchannels", _i), ("nkernels", _i), ("kernel_fn", _i), ("dis_norm", _i)]
 
 _lib = None
 

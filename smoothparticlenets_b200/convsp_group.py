@@ -1,0 +1,128 @@
+"""ConvSPGroup -- several ConvSP layers evaluated in one pass over shared neighbour lists.
+
+An opt-in extension, not part of the reference API: the solver iteration of
+the reference's fluid simulation evaluates 9 ConvSP layers on the same ``(locs, neighbors)``
+(examples/fluid_sim.py:367-397); each layer call re-reads the lists, re-gathers the neighbour
+positions and recomputes every distance.  ``ConvSPGroup([layer_a, layer_b, ...])(locs, [data_a,
+data_b, ...], neighbors)`` returns exactly what ``[layer_a(locs, data_a, neighbors), ...]`` returns
+(same values within fp32 rounding, same gradients), but walks the lists once per group.
+
+Requirements for the fused path: every layer has kernel_size 1, the same ndim and radius, no query
+locations (the particles are their own queries), no trainable weights that need gradients, and the
+channel layout is one of the compiled-in signatures (csrc/convsp_group.cu).  Anything else silently
+runs the ordinary per-layer path, so the module is always safe to use.
+"""
+import ctypes
+
+import torch
+
+from . import _native as nat
+from .convsp import ConvSP
+
+
+class ConvSPGroup(torch.nn.Module):
+
+    def __init__(self, layers):
+        super(ConvSPGroup, self).__init__()
+        layers = list(layers)
+        if not layers or not all(isinstance(l, ConvSP) for l in layers):
+            raise ValueError("ConvSPGroup needs a non-empty list of ConvSP layers")
+        self.layers = torch.nn.ModuleList(layers)
+        l0 = layers[0]
+        self._fusable = (len(layers) <= 6 and
+                         all(l.ncells == 1 and l.ndim == l0.ndim and float(l.radius) == float(l0.radius)
+                             for l in layers))
+
+    def forward(self, locs, datas, neighbors):
+        """locs BxNxD, datas: one BxNxC_l tensor per layer, neighbors BxNxK.  Returns a tuple with one
+        BxNxO_l tensor per layer."""
+        layers = list(self.layers)
+        if len(datas) != len(layers):
+            raise ValueError("ConvSPGroup: expected %d data tensors, got %d" % (len(layers), len(datas)))
+        fused = self._fusable and locs.is_cuda and neighbors.shape[1] == locs.shape[1]
+        if fused:
+            for l in layers:
+                if l.weight.requires_grad and torch.is_grad_enabled():
+                    fused = False  # d(weight) is only produced by the per-layer kernels
+        if fused:
+            locs_c = locs.contiguous()
+            datas_c = [d.contiguous() for d in datas]
+            sym_flag = getattr(neighbors, "_spnb_sym_flag", None)
+            cfg = tuple((l.kernel_fn, l.dis_norm, l.nchannels, l.nkernels) for l in layers)
+            flat = list(datas_c) + [l.weight for l in layers] + [l.bias for l in layers]
+            if _supported(locs_c, datas_c, layers, cfg):
+                return _ConvSPGroupFunction.apply(locs_c, neighbors.contiguous(), sym_flag,
+                                                  float(layers[0].radius), cfg, *flat)
+        return tuple(l(locs, d, neighbors) for l, d in zip(layers, datas))
+
+
+def _layer_array(locs, datas, weights, biases, cfg, outs=None, gos=None, ddatas=None):
+    n = len(cfg)
+    arr = (nat.GroupLayer * n)()
+    for i, (fn, dn, C, O) in enumerate(cfg):
+        arr[i].data = nat.ptr(datas[i])
+        arr[i].weight = nat.ptr(weights[i])
+        arr[i].bias = nat.ptr(biases[i]) if biases is not None else None
+        arr[i].out = nat.ptr(outs[i]) if outs is not None else None
+        arr[i].grad_out = nat.ptr(gos[i]) if gos is not None else None
+        arr[i].ddata = nat.ptr(ddatas[i]) if ddatas is not None else None
+        arr[i].nchannels, arr[i].nkernels, arr[i].kernel_fn, arr[i].dis_norm = C, O, fn, dn
+    return arr
+
+
+def _supported(locs, datas, layers, cfg):
+    B, N, D = locs.shape
+    arr = _layer_array(locs, datas, [l.weight for l in layers], None, cfg)
+    return nat.lib().spnb_convsp_group_workspace_bytes(nat.ptr(locs), B, N, D, float(layers[0].radius),
+                                                       len(cfg), arr, 0) > 0
+
+
+class _ConvSPGroupFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, locs, neighbors, sym_flag, radius, cfg, *flat):
+        n = len(cfg)
+        datas, weights, biases = flat[:n], flat[n:2 * n], flat[2 * n:3 * n]
+        for t in (locs, neighbors) + tuple(flat):
+            nat.require_cuda_f32(t, "ConvSPGroup operand")
+        B, N, D = locs.shape
+        K = neighbors.shape[2]
+        L = nat.lib()
+        outs = [torch.empty(B, N, c[3], device=locs.device, dtype=torch.float32) for c in cfg]
+        arr = _layer_array(locs, datas, weights, biases, cfg, outs=outs)
+        wsb = L.spnb_convsp_group_workspace_bytes(nat.ptr(locs), B, N, D, radius, n, arr, 0)
+        ws = torch.empty((wsb + 3) // 4, device=locs.device, dtype=torch.float32)
+        with torch.cuda.device(locs.device):
+            nat.check(L.spnb_convsp_group_forward(nat.ptr(locs), nat.ptr(neighbors), B, N, D, K, radius, n,
+                                                  arr, nat.ptr(ws), wsb, nat.stream()),
+                      "spnb_convsp_group_forward")
+        ctx.save_for_backward(locs, neighbors, *datas, *weights)
+        ctx.cfg, ctx.radius, ctx.sym_flag = cfg, radius, sym_flag
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grad_outs):
+        cfg, radius = ctx.cfg, ctx.radius
+        n = len(cfg)
+        saved = ctx.saved_tensors
+        locs, neighbors = saved[0], saved[1]
+        datas, weights = saved[2:2 + n], saved[2 + n:2 + 2 * n]
+        B, N, D = locs.shape
+        K = neighbors.shape[2]
+        dev = locs.device
+        gos = [g.contiguous() if g is not None else torch.zeros(B, N, cfg[i][3], device=dev)
+               for i, g in enumerate(grad_outs)]
+        need_locs = ctx.needs_input_grad[0]
+        need_data = ctx.needs_input_grad[5:5 + n]
+        dlocs = torch.empty(B, N, D, device=dev, dtype=torch.float32)
+        ddatas = [torch.empty_like(datas[i]) if need_data[i] else None for i in range(n)]
+        L = nat.lib()
+        arr = _layer_array(locs, datas, weights, None, cfg, gos=gos, ddatas=ddatas)
+        wsb = L.spnb_convsp_group_workspace_bytes(nat.ptr(locs), B, N, D, radius, n, arr, 1)
+        ws = torch.empty((wsb + 3) // 4, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            nat.check(L.spnb_convsp_group_backward(nat.ptr(locs), nat.ptr(neighbors), B, N, D, K, radius, n,
+                                                   arr, nat.ptr(dlocs), nat.ptr(ctx.sym_flag), nat.ptr(ws),
+                                                   wsb, nat.stream()), "spnb_convsp_group_backward")
+        dbias = [gos[i].sum(1).sum(0) if ctx.needs_input_grad[5 + 2 * n + i] else None for i in range(n)]
+        return (dlocs if need_locs else None, None, None, None, None) + tuple(ddatas) + (None,) * n + tuple(dbias)

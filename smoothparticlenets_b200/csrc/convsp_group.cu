@@ -1,0 +1,667 @@
+// Fused ConvSP "group": several ConvSP layers that share (locs, neighbors, radius) -- and have
+// kernel_size 1 -- evaluated in ONE walk over the neighbour lists.
+//
+// This is SURVEY.md section 8(f) rank 1: the solver iteration of the reference's fluid simulation calls
+// 9 ConvSP layers on the same particle set (examples/fluid_sim.py:367-397); each per-layer kernel
+// re-reads the neighbour list, re-gathers the neighbour positions and recomputes the distance.  The
+// math per layer is unchanged (compute_kernel_cells, src/common_funcs.h:439-583, ncells = 1):
+//     out_l[i,o] = bias_l[o] + sum_c w_l[o,c] * sum_j W_l(d_ij) * norm_l(d_ij) * data_l[j,c]
+//
+// Design:
+//  * a PACK pre-pass writes one 16-byte aligned record per particle: position, the distinct data
+//    tensors of the group (a data tensor that IS the position tensor is not duplicated) and, for the
+//    backward pass, U_l[n,c] = sum_o grad_out_l[n,o] * w_l[o,c].  The main kernel then gathers each
+//    neighbour with a few LDG.128 instead of many scalar loads from separate tensors;
+//  * the main kernels walk the rows exactly like convsp_small.cu (8 lanes per query, 32 entries in
+//    flight, exact in-radius predicate, fast fp32 after it); per pair the geometry is computed once,
+//    W / dW once per distinct (kernel, dis_norm), and only C_l FMAs per layer are spent on channels
+//    because the weights are applied once per query in the epilogue (forward) or folded into U_l
+//    (backward);
+//  * backward: symmetric-gather (no atomics) when the device flag allows, else scatter with float
+//    atomics -- same rule as the per-layer kernels.  d(weight) is not produced here; groups whose
+//    layers need it fall back to the per-layer kernels in the Python layer.
+//
+// The channel layout of a group is a compile-time signature (template parameters), so every record
+// field and accumulator lives in a register.  Signatures used by the fluid step are instantiated at
+// the bottom; anything else reports "unsupported" and the caller uses the per-layer path.
+#include <string.h>
+
+#include "convsp_small.cuh"
+
+namespace spnb {
+
+namespace {
+
+constexpr int kG = 8, kThreads = 256, kEPL = 4, kChunk = kG * kEPL;
+constexpr int kMaxLayers = 6;
+constexpr unsigned kSrcLocs = 15;  // "data is the position tensor"
+
+// ---- compile-time group signature -------------------------------------------------------------------
+// CS: 4 bits per layer = in-channels C_l;  SS: 4 bits per layer = index of the distinct data tensor
+// feeding the layer, or kSrcLocs;  FS: 4 bits per layer = kernel id;  NS: 1 bit per layer = dis_norm.
+// Kernel ids are compile-time so that W / dW are straight-line code (a run-time switch per layer and
+// pair costs more than the arithmetic itself and blows the instruction cache -- measured).
+__host__ __device__ constexpr int deriv_expr_ct(int fn)
+{
+    return fn == E_DEFAULT ? E_DDEFAULT : fn == E_DDEFAULT ? E_DDEFAULT2 : fn == E_DDEFAULT2 ? E_D_DDEFAULT2
+         : fn == E_PRESSURE ? E_DPRESSURE : fn == E_DPRESSURE ? E_DPRESSURE2 : fn == E_DPRESSURE2 ? E_D_DPRESSURE2
+         : fn == E_INDIRECT ? E_D_INDIRECT : fn == E_CONSTANT ? E_D_CONSTANT : fn == E_SPIKY ? E_DSPIKY
+         : fn == E_DSPIKY ? E_D_DSPIKY : fn == E_COHESION ? E_D_COHESION : fn == E_SIGMOID ? E_D_SIGMOID
+         : E_D_CONSTANT;
+}
+
+template <int D_, int NL_, unsigned CS_, unsigned SS_, unsigned FS_, unsigned NS_>
+struct Sig {
+    static constexpr int D = D_, NL = NL_;
+    static __host__ __device__ constexpr int FN(int l) { return (FS_ >> (4 * l)) & 15; }
+    static __host__ __device__ constexpr int DFN(int l) { return deriv_expr_ct(FN(l)); }
+    static __host__ __device__ constexpr int NORM(int l) { return (NS_ >> l) & 1; }
+    static __host__ __device__ constexpr int SAL(int l)  // first layer with the same (kernel, dis_norm)
+    {
+        for (int m = 0; m < l; ++m)
+            if (FN(m) == FN(l) && NORM(m) == NORM(l)) return m;
+        return l;
+    }
+    static __host__ __device__ constexpr int C(int l) { return (CS_ >> (4 * l)) & 15; }
+    static __host__ __device__ constexpr int S(int l) { return (SS_ >> (4 * l)) & 15; }
+    static __host__ __device__ constexpr int nsrc()
+    {
+        int n = 0;
+        for (int l = 0; l < NL_; ++l)
+            if (S(l) != (int)kSrcLocs && S(l) + 1 > n) n = S(l) + 1;
+        return n;
+    }
+    static __host__ __device__ constexpr int src_channels(int s)
+    {
+        for (int l = 0; l < NL_; ++l)
+            if (S(l) == s) return C(l);
+        return 0;
+    }
+    static __host__ __device__ constexpr int src_off(int s)  // record offset of distinct data tensor s
+    {
+        int o = D_;
+        for (int t = 0; t < s; ++t) o += src_channels(t);
+        return o;
+    }
+    static __host__ __device__ constexpr int data_off(int l) { return S(l) == (int)kSrcLocs ? 0 : src_off(S(l)); }
+    static __host__ __device__ constexpr int ctot()
+    {
+        int n = 0;
+        for (int l = 0; l < NL_; ++l) n += C(l);
+        return n;
+    }
+    static __host__ __device__ constexpr int chan_off(int l)  // offset of layer l in the concatenated channel space
+    {
+        int n = 0;
+        for (int t = 0; t < l; ++t) n += C(t);
+        return n;
+    }
+    static __host__ __device__ constexpr int fwd_floats() { return src_off(nsrc()); }
+    static __host__ __device__ constexpr int u_off(int l) { return fwd_floats() + chan_off(l); }
+    static __host__ __device__ constexpr int bwd_floats() { return fwd_floats() + ctot(); }
+    static __host__ __device__ constexpr int fwd_vec() { return (fwd_floats() + 3) / 4; }
+    static __host__ __device__ constexpr int bwd_vec() { return (bwd_floats() + 3) / 4; }
+};
+
+struct LayerArgs {
+    const float* data;      // [B,N,C]
+    const float* weight;    // [O,C]
+    const float* bias;      // [O] or NULL
+    float* out;             // fwd: [B,N,O]
+    const float* grad_out;  // bwd: [B,N,O]
+    float* ddata;           // bwd: [B,N,C] or NULL
+    int C, O;
+    int w_expr, dw_expr, dis_norm;
+    int salias;             // first layer with the same (kernel, dis_norm)
+    float wc, dwc;
+};
+struct GroupArgs {
+    LayerArgs l[kMaxLayers];
+    const float* src[kMaxLayers];  // distinct data tensors
+    float H, invH, H2, rad2;
+};
+
+struct SphF { float H, invH, H2; };
+
+__device__ __forceinline__ float sph_fast(int e, float d, float d2, float c, const SphF& p)
+{
+    switch (e) {
+    case E_DEFAULT:   { const float q = p.H2 - d2; return c * q * q * q; }
+    case E_DDEFAULT:  { const float q = p.H2 - d2; return c * q * q * d; }
+    case E_DDEFAULT2: return c * (p.H2 * p.H2 + d2 * (5.0f * d2 - 6.0f * p.H2));
+    case E_D_DDEFAULT2: return c * d * (20.0f * d2 - 12.0f * p.H2);
+    case E_PRESSURE:  { const float q = p.H - d; return c * q * q * q; }
+    case E_DPRESSURE: { const float q = p.H - d; return c * q * q; }
+    case E_DPRESSURE2: return c * (p.H - d);
+    case E_D_DPRESSURE2: return c;
+    case E_INDIRECT:  return p.H - d;
+    case E_D_INDIRECT: return -1.0f;
+    case E_CONSTANT:  return 1.0f;
+    case E_D_CONSTANT: return 0.0f;
+    case E_SPIKY:     { const float q = 1.0f - d * p.invH; return c * q * q; }
+    case E_DSPIKY:    return c * (1.0f - d * p.invH);
+    case E_D_DSPIKY:  return c;
+    case E_COHESION:  { const float t = d * p.invH; return (7.0f - 6.0f * t) * t * t - 1.0f; }
+    case E_D_COHESION: return 2.0f * d * (7.0f * p.H - 9.0f * d) * (p.invH * p.invH * p.invH);
+    case E_SIGMOID:   return 1.0f / (1.0f + expf((d - 0.2f * p.H) * 20.0f * p.invH));
+    case E_D_SIGMOID: { const float ex = expf((d - 0.2f * p.H) * 20.0f * p.invH);
+                        return -20.0f * ex * p.invH / ((ex + 1.0f) * (ex + 1.0f)); }
+    default: return 0.0f;
+    }
+}
+
+__device__ __forceinline__ float fast_rsqrt(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void load_entries(const float* __restrict__ row, int p, int K, float* e)
+{
+    if (p - (p & (kG - 1)) + kChunk <= K) {
+#pragma unroll
+        for (int i = 0; i < kEPL; ++i) e[i] = row[p + i * kG];
+    } else {
+#pragma unroll
+        for (int i = 0; i < kEPL; ++i) e[i] = p + i * kG < K ? row[p + i * kG] : -1.0f;
+    }
+}
+
+__device__ __forceinline__ int chunk_valid(const float* e, int lane, int sub, bool& ended)
+{
+    int first = kChunk;
+#pragma unroll
+    for (int i = kEPL - 1; i >= 0; --i) {
+        const unsigned negb = __ballot_sync(0xffffffffu, !(e[i] >= 0.0f));
+        const unsigned g = (negb >> (lane - sub)) & ((1u << kG) - 1u);
+        if (g) first = i * kG + __ffs(g) - 1;
+    }
+    ended = first < kChunk;
+    return first > sub ? (first - sub + kG - 1) / kG : 0;
+}
+
+template <typename T>
+__device__ __forceinline__ T group_sum(T v)
+{
+#pragma unroll
+    for (int o = kG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- pack pre-pass ----------------------------------------------------------------------------------
+// rec[n] = [ locs(D) | distinct data ... | (BWD) U_l(C_l) for every layer ], padded to float4s.
+template <typename SG, bool BWD>
+__global__ void __launch_bounds__(256)
+k_group_pack(const float* __restrict__ locs, GroupArgs ga, long long BN, float* __restrict__ rec)
+{
+    constexpr int V = BWD ? SG::bwd_vec() : SG::fwd_vec();
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= BN) return;
+    float r[V * 4];
+#pragma unroll
+    for (int i = 0; i < V * 4; ++i) r[i] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < SG::D; ++k) r[k] = locs[n * SG::D + k];
+#pragma unroll
+    for (int s = 0; s < SG::nsrc(); ++s)
+#pragma unroll
+        for (int c = 0; c < SG::src_channels(s); ++c)
+            r[SG::src_off(s) + c] = ga.src[s][n * SG::src_channels(s) + c];
+    if (BWD) {
+#pragma unroll
+        for (int l = 0; l < SG::NL; ++l) {
+            const LayerArgs& L = ga.l[l];
+            for (int o = 0; o < L.O; ++o) {
+                const float g = L.grad_out[n * L.O + o];
+#pragma unroll
+                for (int c = 0; c < SG::C(l); ++c)
+                    r[SG::u_off(l) + c] = fmaf(g, L.weight[o * SG::C(l) + c], r[SG::u_off(l) + c]);
+            }
+        }
+    }
+    float4* dst = reinterpret_cast<float4*>(rec) + n * V;
+#pragma unroll
+    for (int v = 0; v < V; ++v) dst[v] = make_float4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+}
+
+// s_l = W_l(d) * norm_l (and t_l = dW_l/dd / d * norm_l) for every layer, evaluated once per distinct
+// (kernel, dis_norm); everything about the layer list is a compile-time constant.
+template <typename SG, bool WITH_T>
+__device__ __forceinline__ void layer_scales(const GroupArgs& ga, const SphF& sp, float d, float d2,
+                                             float inv, bool pos, float* s, float* t)
+{
+#pragma unroll
+    for (int l = 0; l < SG::NL; ++l) {
+        if (SG::SAL(l) == l) {
+            const float norm = (SG::NORM(l) && pos) ? inv : 1.0f;
+            s[l] = sph_fast(SG::FN(l), d, d2, ga.l[l].wc, sp) * norm;
+            if (WITH_T) t[l] = pos ? sph_fast(SG::DFN(l), d, d2, ga.l[l].dwc, sp) * inv * norm : 0.0f;
+        } else {
+            s[l] = s[SG::SAL(l)];
+            if (WITH_T) t[l] = t[SG::SAL(l)];
+        }
+    }
+}
+
+// ---- forward ----------------------------------------------------------------------------------------
+template <typename SG>
+__global__ void __launch_bounds__(kThreads)
+k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N,
+            int K)
+{
+    constexpr int D = SG::D, V = SG::fwd_vec(), CT = SG::ctot();
+    const int lane = threadIdx.x & 31, sub = lane & (kG - 1);
+    const int b = blockIdx.y;
+    const int m = (blockIdx.x * kThreads + threadIdx.x) / kG;
+    const bool active = m < N;
+    const long long q = (long long)b * N + (active ? m : 0);
+    const SphF sp = {ga.H, ga.invH, ga.H2};
+    const float4* srec = reinterpret_cast<const float4*>(rec) + (size_t)b * N * V;
+    float x[D];
+    {
+        const float4 r0 = srec[(size_t)(active ? m : 0) * V];
+        const float t[4] = {r0.x, r0.y, r0.z, r0.w};
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[k] = t[k];
+    }
+    const float* row = neighbors + q * K;
+    float G[CT];
+#pragma unroll
+    for (int i = 0; i < CT; ++i) G[i] = 0.0f;
+
+    float e[kEPL], nxt[kEPL];
+#pragma unroll
+    for (int i = 0; i < kEPL; ++i) e[i] = nxt[i] = -1.0f;
+    if (active) load_entries(row, sub, K, e);
+    for (int base = 0; base < K; base += kChunk) {
+        bool ended;
+        const int nvalid = chunk_valid(e, lane, sub, ended);
+        if (!ended && base + kChunk < K) load_entries(row, base + kChunk + sub, K, nxt);
+        const int maxvalid = __reduce_max_sync(0xffffffffu, nvalid);
+        float r[kEPL][V * 4];
+#pragma unroll
+        for (int i = 0; i < kEPL; ++i) {
+            if (i >= maxvalid) continue;
+            const unsigned j = i < nvalid ? (unsigned)(int)e[i] : 0u;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float4 t = srec[j * (unsigned)V + v];
+                r[i][4 * v] = t.x; r[i][4 * v + 1] = t.y; r[i][4 * v + 2] = t.z; r[i][4 * v + 3] = t.w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kEPL; ++i) {
+            if (i >= maxvalid) continue;
+            float d2 = 0.0f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float nr = x[k] - r[i][k];
+                d2 += nr * nr;
+            }
+            if (i < nvalid && d2 < ga.rad2) {
+                const bool pos = d2 > 0.0f;
+                const float inv = fast_rsqrt(d2);
+                const float d = pos ? d2 * inv : 0.0f;
+                float s[SG::NL];
+                layer_scales<SG, false>(ga, sp, d, d2, inv, pos, s, nullptr);
+#pragma unroll
+                for (int l = 0; l < SG::NL; ++l)
+#pragma unroll
+                    for (int c = 0; c < SG::C(l); ++c)
+                        G[SG::chan_off(l) + c] = fmaf(s[l], r[i][SG::data_off(l) + c], G[SG::chan_off(l) + c]);
+            }
+        }
+        if (__all_sync(0xffffffffu, ended)) break;
+#pragma unroll
+        for (int i = 0; i < kEPL; ++i) {
+            e[i] = nxt[i];
+            nxt[i] = -1.0f;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CT; ++i) G[i] = group_sum(G[i]);
+    // epilogue: apply the weights once per query; the 8 lanes of the group split the outputs
+    if (active) {
+#pragma unroll
+        for (int l = 0; l < SG::NL; ++l) {
+            const LayerArgs& L = ga.l[l];
+            for (int o = sub; o < L.O; o += kG) {
+                float v = L.bias ? L.bias[o] : 0.0f;
+#pragma unroll
+                for (int c = 0; c < SG::C(l); ++c) v = fmaf(L.weight[o * SG::C(l) + c], G[SG::chan_off(l) + c], v);
+                L.out[q * L.O + o] = v;
+            }
+        }
+    }
+}
+
+// ---- backward ---------------------------------------------------------------------------------------
+// dlocs [B,N,D]: d(sum_l loss_l)/d(locs) through the geometry (query role + neighbour role).
+// ddata_l [B,N,C_l] (may be NULL).  sym: gather; else scatter with atomics into zero-filled buffers.
+template <typename SG>
+__global__ void __launch_bounds__(kThreads, 2)
+k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N,
+            int K, float* dlocs, const int* sym_flag)
+{
+    constexpr int D = SG::D, V = SG::bwd_vec(), CT = SG::ctot();
+    const bool sym = sym_flag != nullptr && *sym_flag == 0;
+    const int lane = threadIdx.x & 31, sub = lane & (kG - 1);
+    const int b = blockIdx.y;
+    const int m = (blockIdx.x * kThreads + threadIdx.x) / kG;
+    const bool active = m < N;
+    const long long q = (long long)b * N + (active ? m : 0);
+    const SphF sp = {ga.H, ga.invH, ga.H2};
+    const float4* srec = reinterpret_cast<const float4*>(rec) + (size_t)b * N * V;
+    float me[V * 4];  // my own record: position, data_l[i], U_l[i]
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const float4 t = srec[(size_t)(active ? m : 0) * V + v];
+        me[4 * v] = t.x; me[4 * v + 1] = t.y; me[4 * v + 2] = t.z; me[4 * v + 3] = t.w;
+    }
+    const float* row = neighbors + q * K;
+    float a_dl[D], a_dd[CT];
+#pragma unroll
+    for (int k = 0; k < D; ++k) a_dl[k] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < CT; ++i) a_dd[i] = 0.0f;
+
+    float e[kEPL], nxt[kEPL];
+#pragma unroll
+    for (int i = 0; i < kEPL; ++i) e[i] = nxt[i] = -1.0f;
+    if (active) load_entries(row, sub, K, e);
+    for (int base = 0; base < K; base += kChunk) {
+        bool ended;
+        const int nvalid = chunk_valid(e, lane, sub, ended);
+        if (!ended && base + kChunk < K) load_entries(row, base + kChunk + sub, K, nxt);
+        const int maxvalid = __reduce_max_sync(0xffffffffu, nvalid);
+#pragma unroll 2
+        for (int i = 0; i < kEPL; ++i) {
+            if (i >= maxvalid) continue;
+            const unsigned j = i < nvalid ? (unsigned)(int)e[i] : 0u;
+            float r[V * 4];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float4 t = srec[j * (unsigned)V + v];
+                r[4 * v] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
+            }
+            float disp[D];
+            float d2 = 0.0f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                disp[k] = me[k] - r[k];
+                d2 += disp[k] * disp[k];
+            }
+            if (i < nvalid && d2 < ga.rad2) {
+                const bool pos = d2 > 0.0f;
+                const float inv = fast_rsqrt(d2);
+                const float d = pos ? d2 * inv : 0.0f;
+                float s[SG::NL], t[SG::NL];
+                layer_scales<SG, true>(ga, sp, d, d2, inv, pos, s, t);
+                float TA = 0.0f, TB = 0.0f;  // position-gradient coefficients of the two pair roles
+#pragma unroll
+                for (int l = 0; l < SG::NL; ++l) {
+                    float A = 0.0f, Bv = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < SG::C(l); ++c) {
+                        // pair (i, j): U_l[i] . data_l[j]      pair (j, i): U_l[j] . data_l[i]
+                        A = fmaf(me[SG::u_off(l) + c], r[SG::data_off(l) + c], A);
+                        Bv = fmaf(r[SG::u_off(l) + c], me[SG::data_off(l) + c], Bv);
+                        if (sym) a_dd[SG::chan_off(l) + c] = fmaf(s[l], r[SG::u_off(l) + c], a_dd[SG::chan_off(l) + c]);
+                    }
+                    TA = fmaf(A, t[l], TA);
+                    TB = fmaf(Bv, t[l], TB);
+                }
+                if (sym) {
+                    const float T = TA + TB;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) a_dl[k] = fmaf(T, disp[k], a_dl[k]);
+                } else {
+                    const size_t jo = (size_t)b * N + j;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        a_dl[k] = fmaf(TA, disp[k], a_dl[k]);
+                        if (pos) atomicAdd(dlocs + jo * D + k, -TA * disp[k]);
+                    }
+#pragma unroll
+                    for (int l = 0; l < SG::NL; ++l) {
+                        if (ga.l[l].ddata) {
+#pragma unroll
+                            for (int c = 0; c < SG::C(l); ++c)
+                                atomicAdd(ga.l[l].ddata + jo * SG::C(l) + c, s[l] * me[SG::u_off(l) + c]);
+                        }
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, ended)) break;
+#pragma unroll
+        for (int i = 0; i < kEPL; ++i) {
+            e[i] = nxt[i];
+            nxt[i] = -1.0f;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) a_dl[k] = group_sum(a_dl[k]);
+    if (sym) {
+#pragma unroll
+        for (int i = 0; i < CT; ++i) a_dd[i] = group_sum(a_dd[i]);
+    }
+    if (active && sub == 0) {
+        if (sym) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) dlocs[q * D + k] = a_dl[k];
+#pragma unroll
+            for (int l = 0; l < SG::NL; ++l) {
+                if (ga.l[l].ddata) {
+#pragma unroll
+                    for (int c = 0; c < SG::C(l); ++c) ga.l[l].ddata[q * SG::C(l) + c] = a_dd[SG::chan_off(l) + c];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < D; ++k) atomicAdd(dlocs + q * D + k, a_dl[k]);
+        }
+    }
+}
+
+// ---- host -------------------------------------------------------------------------------------------
+struct Signature {
+    int D, NL;
+    unsigned CS, SS, FS, NS;
+};
+
+// Distinct-data numbering and (kernel, dis_norm) aliases of a host-side layer list.
+static bool make_signature(const float* locs, int D, int nl, const SpnbGroupLayer* layers, Signature& sg,
+                           GroupArgs& ga, float radius)
+{
+    if (nl < 1 || nl > kMaxLayers) return false;
+    sg.D = D;
+    sg.NL = nl;
+    sg.CS = sg.SS = sg.FS = sg.NS = 0;
+    int nsrc = 0;
+    for (int l = 0; l < nl; ++l) {
+        const SpnbGroupLayer& L = layers[l];
+        if (L.nchannels < 1 || L.nchannels > 4 || L.nkernels < 1) return false;
+        unsigned s = kSrcLocs;
+        if (L.data != locs || L.nchannels != D) {
+            int found = -1;
+            for (int t = 0; t < nsrc; ++t)
+                if (ga.src[t] == L.data) found = t;
+            if (found < 0) {
+                // a distinct tensor must have the same channel count for every layer that uses it
+                found = nsrc;
+                ga.src[nsrc++] = L.data;
+            }
+            s = (unsigned)found;
+        }
+        sg.CS |= (unsigned)L.nchannels << (4 * l);
+        sg.SS |= s << (4 * l);
+        sg.FS |= (unsigned)L.kernel_fn << (4 * l);
+        sg.NS |= (L.dis_norm ? 1u : 0u) << l;
+        const SphParams p = make_sph_params(L.kernel_fn, radius);
+        LayerArgs& A = ga.l[l];
+        A.data = L.data; A.weight = L.weight; A.bias = L.bias; A.out = L.out;
+        A.grad_out = L.grad_out; A.ddata = L.ddata;
+        A.C = L.nchannels; A.O = L.nkernels;
+        A.w_expr = p.w_expr; A.dw_expr = p.dw_expr; A.dis_norm = L.dis_norm ? 1 : 0;
+        double wc = p.w_coef, dwc = p.dw_coef;
+        if (p.w_expr == E_DSPIKY) wc /= (double)radius;
+        if (p.dw_expr == E_DSPIKY) dwc /= (double)radius;
+        A.wc = (float)wc; A.dwc = (float)dwc;
+        A.salias = l;
+        for (int m = 0; m < l; ++m)
+            if (ga.l[m].w_expr == A.w_expr && ga.l[m].dis_norm == A.dis_norm) { A.salias = m; break; }
+    }
+    // same tensor used with different channel counts -> not representable
+    for (int l = 0; l < nl; ++l)
+        for (int m = 0; m < l; ++m)
+            if (((sg.SS >> (4 * l)) & 15) == ((sg.SS >> (4 * m)) & 15) && ((sg.SS >> (4 * l)) & 15) != kSrcLocs &&
+                layers[l].nchannels != layers[m].nchannels)
+                return false;
+    ga.H = radius; ga.invH = 1.0f / radius; ga.H2 = radius * radius; ga.rad2 = radius * radius;
+    return true;
+}
+
+// The instantiated signatures: X(D, NL, CS, SS, FS, NS); layer 0 is the lowest nibble / bit.  Kernel
+// ids: cohesion 0, constant 1, dspiky 7, spiky 0xB (kernels.py:123).  These are the layer groups of
+// the fluid step (fluid_sim.py:367-397,419-420), for ndim 3 and 2:
+//   A: spiky1(ones) dspikyD*(locs) dspiky1*(ones) cohesionD*(locs) cohesion1*(ones) constant1(ones)
+//   B: dspikyD*(locs*pressure) dspiky1*(pressure)      V: spikyD(vel) spiky1(ones)
+//   C: constantD(normals)                               (* = dis_norm)
+#define SPNB_GROUP_SIGS(X)                                  \
+    X(3, 6, 0x113131u, 0x00F0F0u, 0x10077Bu, 0x1Eu)         \
+    X(3, 2, 0x13u, 0x10u, 0x77u, 0x3u)                      \
+    X(3, 2, 0x13u, 0x10u, 0xBBu, 0x0u)                      \
+    X(3, 1, 0x3u, 0x0u, 0x1u, 0x0u)                         \
+    X(2, 6, 0x112121u, 0x00F0F0u, 0x10077Bu, 0x1Eu)         \
+    X(2, 2, 0x12u, 0x10u, 0x77u, 0x3u)                      \
+    X(2, 2, 0x12u, 0x10u, 0xBBu, 0x0u)                      \
+    X(2, 1, 0x2u, 0x0u, 0x1u, 0x0u)
+
+template <typename SG>
+static void run_fwd(const float* locs, const float* neighbors, const GroupArgs& ga, int B, int N, int K,
+                    float* rec, cudaStream_t stream)
+{
+    const long long BN = (long long)B * N;
+    k_group_pack<SG, false><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec);
+    k_group_fwd<SG><<<dim3(cdiv((long long)N * kG, kThreads), B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K);
+}
+template <typename SG>
+static void run_bwd(const float* locs, const float* neighbors, const GroupArgs& ga, int B, int N, int K,
+                    float* rec, float* dlocs, const int* sym_flag, cudaStream_t stream)
+{
+    const long long BN = (long long)B * N;
+    k_group_pack<SG, true><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec);
+    k_group_bwd<SG><<<dim3(cdiv((long long)N * kG, kThreads), B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K,
+                                                                                        dlocs, sym_flag);
+}
+
+static size_t record_floats(const Signature& sg, bool bwd)
+{
+    size_t n = 0;
+#define X(DD, NN, CC, SS_, FF, NO)                                                                 \
+    if (sg.D == DD && sg.NL == NN && sg.CS == CC && sg.SS == SS_ && sg.FS == FF && sg.NS == NO)    \
+        n = 4 * (size_t)(bwd ? Sig<DD, NN, CC, SS_, FF, NO>::bwd_vec() : Sig<DD, NN, CC, SS_, FF, NO>::fwd_vec());
+    SPNB_GROUP_SIGS(X)
+#undef X
+    return n;
+}
+
+}  // namespace
+}  // namespace spnb
+
+using namespace spnb;
+
+extern "C" {
+
+size_t spnb_convsp_group_workspace_bytes(const float* locs, int batch_size, int N, int ndims, float radius,
+                                         int nlayers, const SpnbGroupLayer* layers, int backward)
+{
+    Signature sg;
+    GroupArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    if (!layers || !make_signature(locs, ndims, nlayers, layers, sg, ga, radius)) return 0;
+    return sizeof(float) * record_floats(sg, backward != 0) * (size_t)batch_size * N;
+}
+
+int spnb_convsp_group_forward(const float* locs, const float* neighbors, int B, int N, int D, int K,
+                              float radius, int nlayers, const SpnbGroupLayer* layers, void* workspace,
+                              size_t workspace_bytes, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Signature sg;
+    GroupArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    if (!locs || !neighbors || !layers || B <= 0 || N <= 0 || K <= 0) {
+        set_error("spnb_convsp_group_forward: bad arguments");
+        return 0;
+    }
+    for (int l = 0; l < nlayers; ++l)
+        if (!layers[l].data || !layers[l].weight || !layers[l].out || layers[l].kernel_fn < 0 ||
+            layers[l].kernel_fn >= SPNB_NUM_KERNEL_FNS) {
+            set_error("spnb_convsp_group_forward: layer %d: null pointer or bad kernel id", l);
+            return 0;
+        }
+    const size_t need = make_signature(locs, D, nlayers, layers, sg, ga, radius)
+                            ? sizeof(float) * record_floats(sg, false) * (size_t)B * N : 0;
+    if (need == 0) {
+        set_error("spnb_convsp_group_forward: unsupported group signature");
+        return 0;
+    }
+    if (!workspace || workspace_bytes < need) {
+        set_error("spnb_convsp_group_forward: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return 0;
+    }
+#define X(DD, NN, CC, SS_, FF, NO)                                                                 \
+    if (sg.D == DD && sg.NL == NN && sg.CS == CC && sg.SS == SS_ && sg.FS == FF && sg.NS == NO)    \
+        run_fwd<Sig<DD, NN, CC, SS_, FF, NO>>(locs, neighbors, ga, B, N, K, (float*)workspace, stream);
+    SPNB_GROUP_SIGS(X)
+#undef X
+    count_launches(2);
+    return check_launch("spnb_convsp_group_forward") ? 1 : 0;
+}
+
+int spnb_convsp_group_backward(const float* locs, const float* neighbors, int B, int N, int D, int K,
+                               float radius, int nlayers, const SpnbGroupLayer* layers, float* dlocs,
+                               const int* sym_flag, void* workspace, size_t workspace_bytes, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Signature sg;
+    GroupArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    if (!locs || !neighbors || !layers || !dlocs || B <= 0 || N <= 0 || K <= 0) {
+        set_error("spnb_convsp_group_backward: bad arguments");
+        return 0;
+    }
+    for (int l = 0; l < nlayers; ++l)
+        if (!layers[l].data || !layers[l].weight || !layers[l].grad_out || layers[l].kernel_fn < 0 ||
+            layers[l].kernel_fn >= SPNB_NUM_KERNEL_FNS) {
+            set_error("spnb_convsp_group_backward: layer %d: null pointer or bad kernel id", l);
+            return 0;
+        }
+    const size_t need = make_signature(locs, D, nlayers, layers, sg, ga, radius)
+                            ? sizeof(float) * record_floats(sg, true) * (size_t)B * N : 0;
+    if (need == 0) {
+        set_error("spnb_convsp_group_backward: unsupported group signature");
+        return 0;
+    }
+    if (!workspace || workspace_bytes < need) {
+        set_error("spnb_convsp_group_backward: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return 0;
+    }
+    // scatter targets start from zero (the gather mode overwrites; which one runs is a device decision)
+    cudaMemsetAsync(dlocs, 0, sizeof(float) * (size_t)B * N * D, stream);
+    for (int l = 0; l < nlayers; ++l)
+        if (layers[l].ddata)
+            cudaMemsetAsync(layers[l].ddata, 0, sizeof(float) * (size_t)B * N * layers[l].nchannels, stream);
+#define X(DD, NN, CC, SS_, FF, NO)                                                                 \
+    if (sg.D == DD && sg.NL == NN && sg.CS == CC && sg.SS == SS_ && sg.FS == FF && sg.NS == NO)    \
+        run_bwd<Sig<DD, NN, CC, SS_, FF, NO>>(locs, neighbors, ga, B, N, K, (float*)workspace, dlocs, sym_flag, stream);
+    SPNB_GROUP_SIGS(X)
+#undef X
+    count_launches(2);
+    return check_launch("spnb_convsp_group_backward") ? 1 : 0;
+}
+
+}  // extern "C"

@@ -26,7 +26,7 @@ from smoothparticlenets_b200 import _native as nat  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="fwd1,fwd3,bwd1,bwd3,collide,search,reorder")
+    ap.add_argument("--only", default="fwd1,fwd3,bwd1,bwd3,collide,search,reorder,gA_fwd,gA_fb,gB_fwd,gB_fb,gV_fwd")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--scenes", type=int, default=8)
     ap.add_argument("--particles", type=int, default=65536)
@@ -86,6 +86,30 @@ def main():
     def reorder():
         L.spnb_reorder_data(nat.ptr(locs), nat.ptr(vel), nat.ptr(idxs), nat.ptr(ro_l), nat.ptr(ro_v), B, N, D, 3, 0, st)
 
+    # fused groups (ConvSPGroup) of the fluid step: forward and forward+backward through autograd
+    model_f = fluidstep.FluidStep(spn, radius=R, max_collisions=K, fused=True).cuda()
+    press = torch.rand(B, N, 1, device="cuda")
+
+    def group_fwd(group, mk):
+        def run():
+            with torch.no_grad():
+                group(sl, mk(sl), nb)
+        return run
+
+    def group_fb(group, mk):
+        l = sl.detach().clone().requires_grad_(True)
+        outs0 = group(l, mk(l), nb)
+        gos = [torch.rand_like(o) for o in outs0]
+
+        def run():
+            outs = group(l, mk(l), nb)
+            torch.autograd.grad(outs, [l], gos)
+        return run
+
+    mkA = lambda l: [ones, l, ones, l, ones, ones]
+    mkB = lambda l: [l * press, press]
+    mkV = lambda l: [sv, ones]
+
     P = B * N
     fb = lambda C, O: 4 * D + 4 * C + 4 * (nbar + 1) + 4 * O
     bb = lambda C, O: fb(C, O) + 8 * D + 4 * C
@@ -95,6 +119,11 @@ def main():
         "collide": (collide, P * (4 * D + 4 + 4 * K)),
         "search": (search, P * (12 + 20 + 52 + 528)),
         "reorder": (reorder, P * 52),
+        "gA_fwd": (group_fwd(model_f.group_a, mkA), P * (2 * fb(1, 1) * 2 + 2 * fb(3, 3))),
+        "gA_fb": (group_fb(model_f.group_a, mkA), P * (4 * (fb(1, 1) + bb(1, 1)) + 2 * (fb(3, 3) + bb(3, 3)))),
+        "gB_fwd": (group_fwd(model_f.group_b, mkB), P * (fb(1, 1) + fb(3, 3))),
+        "gB_fb": (group_fb(model_f.group_b, mkB), P * (fb(1, 1) + bb(1, 1) + fb(3, 3) + bb(3, 3))),
+        "gV_fwd": (group_fwd(model_f.group_v, mkV), P * (fb(1, 1) + fb(3, 3))),
     }
     print("nbar %.2f  peak %.0f GB/s" % (nbar, peak))
     for name, (fn, byts) in table.items():
