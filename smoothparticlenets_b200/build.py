@@ -1,16 +1,20 @@
 """Builds libspnb.so -- the sm_100a CUDA library behind the C ABI in include/spnb.h.
 
-    python -m smoothparticlenets_b200.build [--force] [--verbose]
+    python -m smoothparticlenets_b200.build [--force] [--verbose] [--ptxas]
 
-nvcc cross-compiles without a GPU.  The library is built IN-TREE (next to this file) so that it
-travels with the repository snapshot to the GPU box; it is git-ignored.
+nvcc cross-compiles without a GPU.  Sources are compiled to objects in parallel (cached by content +
+flags under csrc/_obj/) and linked IN-TREE next to this file so that the library travels with the
+repository snapshot to the GPU box; objects and library are git-ignored.
 """
+import concurrent.futures
+import hashlib
 import os
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 LIB_PATH = os.path.join(HERE, "libspnb.so")
 SOURCES = ["common.cu", "hashgrid.cu", "convsp.cu", "convsp_small.cu", "convsp_group.cu", "convsdf.cu"]
 
@@ -21,7 +25,6 @@ NVCC_FLAGS = [
     # reference's CPU build bit for bit (no FMA contraction, precise div/sqrt, no fast-math).
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC,-O2,-ffp-contract=off",
-    "-shared",
 ]
 
 
@@ -30,24 +33,62 @@ def _nvcc():
     return cand if os.path.exists(cand) else "nvcc"
 
 
-def needs_build():
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps.append(os.path.join(os.path.dirname(HERE), "include", "spnb.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(os.path.dirname(HERE), "include", "spnb.h"))
+    return hs
+
+
+def _digest(src, flags):
+    h = hashlib.sha1()
+    h.update(" ".join(flags).encode())
+    for path in [src] + _headers():
+        with open(path, "rb") as fp:
+            h.update(fp.read())
+    return h.hexdigest()[:16]
+
+
+def _compile(src, flags, verbose):
+    name = os.path.splitext(os.path.basename(src))[0]
+    obj = os.path.join(OBJ, "%s.%s.o" % (name, _digest(src, flags)))
+    if not os.path.exists(obj):
+        for old in os.listdir(OBJ):
+            if old.startswith(name + "."):
+                os.remove(os.path.join(OBJ, old))
+        cmd = [_nvcc()] + flags + ["-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if verbose or out.returncode != 0:
+            sys.stdout.write(out.stdout)
+        if out.returncode != 0:
+            raise RuntimeError("nvcc failed on %s" % src)
+    return obj
 
 
 def build_library(force=False, verbose=False, extra_flags=()):
-    if not force and not needs_build():
-        return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags)
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    flags = NVCC_FLAGS + list(extra_flags) + os.environ.get("SPNB_NVCC_EXTRA", "").split()
+    os.makedirs(OBJ, exist_ok=True)
+    if force:
+        for old in os.listdir(OBJ):
+            os.remove(os.path.join(OBJ, old))
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(lambda s: _compile(s, flags, verbose), srcs))
+    stamp = os.path.join(OBJ, "link.stamp")
+    key = " ".join(objs)
+    if force or not os.path.exists(LIB_PATH) or not os.path.exists(stamp) or open(stamp).read() != key:
+        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB_PATH]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+        with open(stamp, "w") as fp:
+            fp.write(key)
     return LIB_PATH
+
+
+def needs_build():
+    return not os.path.exists(LIB_PATH)
 
 
 if __name__ == "__main__":

@@ -12,8 +12,8 @@
 //    tensors of the group (a data tensor that IS the position tensor is not duplicated) and, for the
 //    backward pass, U_l[n,c] = sum_o grad_out_l[n,o] * w_l[o,c].  The main kernel then gathers each
 //    neighbour with a few LDG.128 instead of many scalar loads from separate tensors;
-//  * the main kernels walk the rows exactly like convsp_small.cu (8 lanes per query, 32 entries in
-//    flight, exact in-radius predicate, fast fp32 after it); per pair the geometry is computed once,
+//  * the main kernels walk the rows with list_walk.cuh (one thread per query, rows staged through
+//    shared memory, exact in-radius predicate, fast fp32 after it); per pair the geometry is computed once,
 //    W / dW once per distinct (kernel, dis_norm), and only C_l FMAs per layer are spent on channels
 //    because the weights are applied once per query in the epilogue (forward) or folded into U_l
 //    (backward);
@@ -27,12 +27,27 @@
 #include <string.h>
 
 #include "convsp_small.cuh"
+#include "list_walk.cuh"
 
 namespace spnb {
 
 namespace {
 
-constexpr int kG = 8, kThreads = 256, kEPL = 4, kChunk = kG * kEPL;
+constexpr int kThreads = 128;
+// lanes per query / list entries in flight per lane (see list_walk.cuh); tunable at build time.
+// Defaults from the sweep in profiles/README.md (tools/tune_group.sh): G = 4 with few entries in flight.
+#ifndef SPNB_GROUP_FWD_G
+#define SPNB_GROUP_FWD_G 4
+#endif
+#ifndef SPNB_GROUP_FWD_U
+#define SPNB_GROUP_FWD_U 2
+#endif
+#ifndef SPNB_GROUP_BWD_G
+#define SPNB_GROUP_BWD_G 4
+#endif
+#ifndef SPNB_GROUP_BWD_U
+#define SPNB_GROUP_BWD_U 1
+#endif
 constexpr int kMaxLayers = 6;
 constexpr unsigned kSrcLocs = 15;  // "data is the position tensor"
 
@@ -150,45 +165,6 @@ __device__ __forceinline__ float sph_fast(int e, float d, float d2, float c, con
     }
 }
 
-__device__ __forceinline__ float fast_rsqrt(float x)
-{
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-__device__ __forceinline__ void load_entries(const float* __restrict__ row, int p, int K, float* e)
-{
-    if (p - (p & (kG - 1)) + kChunk <= K) {
-#pragma unroll
-        for (int i = 0; i < kEPL; ++i) e[i] = row[p + i * kG];
-    } else {
-#pragma unroll
-        for (int i = 0; i < kEPL; ++i) e[i] = p + i * kG < K ? row[p + i * kG] : -1.0f;
-    }
-}
-
-__device__ __forceinline__ int chunk_valid(const float* e, int lane, int sub, bool& ended)
-{
-    int first = kChunk;
-#pragma unroll
-    for (int i = kEPL - 1; i >= 0; --i) {
-        const unsigned negb = __ballot_sync(0xffffffffu, !(e[i] >= 0.0f));
-        const unsigned g = (negb >> (lane - sub)) & ((1u << kG) - 1u);
-        if (g) first = i * kG + __ffs(g) - 1;
-    }
-    ended = first < kChunk;
-    return first > sub ? (first - sub + kG - 1) / kG : 0;
-}
-
-template <typename T>
-__device__ __forceinline__ T group_sum(T v)
-{
-#pragma unroll
-    for (int o = kG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
 // ---- pack pre-pass ----------------------------------------------------------------------------------
 // rec[n] = [ locs(D) | distinct data ... | (BWD) U_l(C_l) for every layer ], padded to float4s.
 template <typename SG, bool BWD>
@@ -251,11 +227,15 @@ k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
             int K)
 {
     constexpr int D = SG::D, V = SG::fwd_vec(), CT = SG::ctot();
-    const int lane = threadIdx.x & 31, sub = lane & (kG - 1);
+    constexpr int G = SPNB_GROUP_FWD_G, kU = SPNB_GROUP_FWD_U, QPB = kThreads / G, R = 32 / G;
+    __shared__ WalkSmem<G> s_walk[kThreads / 32];
+    const int warp = threadIdx.x >> 5, sub = threadIdx.x % G;
     const int b = blockIdx.y;
-    const int m = (blockIdx.x * kThreads + threadIdx.x) / kG;
+    const int m = blockIdx.x * QPB + threadIdx.x / G;
     const bool active = m < N;
-    const long long q = (long long)b * N + (active ? m : 0);
+    const size_t q = (size_t)b * N + (active ? m : 0);
+    const int m0 = blockIdx.x * QPB + warp * R;  // first query of this warp
+    const int nrows = min(R, max(0, N - m0));
     const SphF sp = {ga.H, ga.invH, ga.H2};
     const float4* srec = reinterpret_cast<const float4*>(rec) + (size_t)b * N * V;
     float x[D];
@@ -265,41 +245,29 @@ k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
 #pragma unroll
         for (int k = 0; k < D; ++k) x[k] = t[k];
     }
-    const float* row = neighbors + q * K;
-    float G[CT];
+    float G_[CT];
 #pragma unroll
-    for (int i = 0; i < CT; ++i) G[i] = 0.0f;
+    for (int i = 0; i < CT; ++i) G_[i] = 0.0f;
+    const float* warp_rows = neighbors + ((size_t)b * N + min(m0, N - 1)) * K;
 
-    float e[kEPL], nxt[kEPL];
+    walk_rows<G, kU>(warp_rows, K, nrows, s_walk[warp], [&](const int* j, const bool* valid) {
+        float r[kU][V * 4];
 #pragma unroll
-    for (int i = 0; i < kEPL; ++i) e[i] = nxt[i] = -1.0f;
-    if (active) load_entries(row, sub, K, e);
-    for (int base = 0; base < K; base += kChunk) {
-        bool ended;
-        const int nvalid = chunk_valid(e, lane, sub, ended);
-        if (!ended && base + kChunk < K) load_entries(row, base + kChunk + sub, K, nxt);
-        const int maxvalid = __reduce_max_sync(0xffffffffu, nvalid);
-        float r[kEPL][V * 4];
-#pragma unroll
-        for (int i = 0; i < kEPL; ++i) {
-            if (i >= maxvalid) continue;
-            const unsigned j = i < nvalid ? (unsigned)(int)e[i] : 0u;
+        for (int u = 0; u < kU; ++u)
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const float4 t = srec[j * (unsigned)V + v];
-                r[i][4 * v] = t.x; r[i][4 * v + 1] = t.y; r[i][4 * v + 2] = t.z; r[i][4 * v + 3] = t.w;
+                const float4 t = srec[(unsigned)j[u] * (unsigned)V + v];
+                r[u][4 * v] = t.x; r[u][4 * v + 1] = t.y; r[u][4 * v + 2] = t.z; r[u][4 * v + 3] = t.w;
             }
-        }
 #pragma unroll
-        for (int i = 0; i < kEPL; ++i) {
-            if (i >= maxvalid) continue;
+        for (int u = 0; u < kU; ++u) {
             float d2 = 0.0f;
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-                const float nr = x[k] - r[i][k];
+                const float nr = x[k] - r[u][k];
                 d2 += nr * nr;
             }
-            if (i < nvalid && d2 < ga.rad2) {
+            if (valid[u] && d2 < ga.rad2) {
                 const bool pos = d2 > 0.0f;
                 const float inv = fast_rsqrt(d2);
                 const float d = pos ? d2 * inv : 0.0f;
@@ -309,27 +277,23 @@ k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
                 for (int l = 0; l < SG::NL; ++l)
 #pragma unroll
                     for (int c = 0; c < SG::C(l); ++c)
-                        G[SG::chan_off(l) + c] = fmaf(s[l], r[i][SG::data_off(l) + c], G[SG::chan_off(l) + c]);
+                        G_[SG::chan_off(l) + c] = fmaf(s[l], r[u][SG::data_off(l) + c], G_[SG::chan_off(l) + c]);
             }
         }
-        if (__all_sync(0xffffffffu, ended)) break;
+    });
+    // epilogue: apply the weights once per query (the G lanes of a group split the outputs)
+    if (G > 1) {
 #pragma unroll
-        for (int i = 0; i < kEPL; ++i) {
-            e[i] = nxt[i];
-            nxt[i] = -1.0f;
-        }
+        for (int i = 0; i < CT; ++i) G_[i] = group_sum<G>(G_[i]);
     }
-#pragma unroll
-    for (int i = 0; i < CT; ++i) G[i] = group_sum(G[i]);
-    // epilogue: apply the weights once per query; the 8 lanes of the group split the outputs
     if (active) {
 #pragma unroll
         for (int l = 0; l < SG::NL; ++l) {
             const LayerArgs& L = ga.l[l];
-            for (int o = sub; o < L.O; o += kG) {
+            for (int o = sub; o < L.O; o += G) {
                 float v = L.bias ? L.bias[o] : 0.0f;
 #pragma unroll
-                for (int c = 0; c < SG::C(l); ++c) v = fmaf(L.weight[o * SG::C(l) + c], G[SG::chan_off(l) + c], v);
+                for (int c = 0; c < SG::C(l); ++c) v = fmaf(L.weight[o * SG::C(l) + c], G_[SG::chan_off(l) + c], v);
                 L.out[q * L.O + o] = v;
             }
         }
@@ -340,17 +304,21 @@ k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
 // dlocs [B,N,D]: d(sum_l loss_l)/d(locs) through the geometry (query role + neighbour role).
 // ddata_l [B,N,C_l] (may be NULL).  sym: gather; else scatter with atomics into zero-filled buffers.
 template <typename SG>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads)
 k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N,
             int K, float* dlocs, const int* sym_flag)
 {
     constexpr int D = SG::D, V = SG::bwd_vec(), CT = SG::ctot();
+    constexpr int G = SPNB_GROUP_BWD_G, UB = SPNB_GROUP_BWD_U, QPB = kThreads / G, R = 32 / G;
+    __shared__ WalkSmem<G> s_walk[kThreads / 32];
     const bool sym = sym_flag != nullptr && *sym_flag == 0;
-    const int lane = threadIdx.x & 31, sub = lane & (kG - 1);
+    const int warp = threadIdx.x >> 5, sub = threadIdx.x % G;
     const int b = blockIdx.y;
-    const int m = (blockIdx.x * kThreads + threadIdx.x) / kG;
+    const int m = blockIdx.x * QPB + threadIdx.x / G;
     const bool active = m < N;
-    const long long q = (long long)b * N + (active ? m : 0);
+    const size_t q = (size_t)b * N + (active ? m : 0);
+    const int m0 = blockIdx.x * QPB + warp * R;
+    const int nrows = min(R, max(0, N - m0));
     const SphF sp = {ga.H, ga.invH, ga.H2};
     const float4* srec = reinterpret_cast<const float4*>(rec) + (size_t)b * N * V;
     float me[V * 4];  // my own record: position, data_l[i], U_l[i]
@@ -359,40 +327,32 @@ k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
         const float4 t = srec[(size_t)(active ? m : 0) * V + v];
         me[4 * v] = t.x; me[4 * v + 1] = t.y; me[4 * v + 2] = t.z; me[4 * v + 3] = t.w;
     }
-    const float* row = neighbors + q * K;
     float a_dl[D], a_dd[CT];
 #pragma unroll
     for (int k = 0; k < D; ++k) a_dl[k] = 0.0f;
 #pragma unroll
     for (int i = 0; i < CT; ++i) a_dd[i] = 0.0f;
+    const float* warp_rows = neighbors + ((size_t)b * N + min(m0, N - 1)) * K;
 
-    float e[kEPL], nxt[kEPL];
+    walk_rows<G, UB>(warp_rows, K, nrows, s_walk[warp], [&](const int* j, const bool* valid) {
+        float r[UB][V * 4];
 #pragma unroll
-    for (int i = 0; i < kEPL; ++i) e[i] = nxt[i] = -1.0f;
-    if (active) load_entries(row, sub, K, e);
-    for (int base = 0; base < K; base += kChunk) {
-        bool ended;
-        const int nvalid = chunk_valid(e, lane, sub, ended);
-        if (!ended && base + kChunk < K) load_entries(row, base + kChunk + sub, K, nxt);
-        const int maxvalid = __reduce_max_sync(0xffffffffu, nvalid);
-#pragma unroll 2
-        for (int i = 0; i < kEPL; ++i) {
-            if (i >= maxvalid) continue;
-            const unsigned j = i < nvalid ? (unsigned)(int)e[i] : 0u;
-            float r[V * 4];
+        for (int u = 0; u < UB; ++u)
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const float4 t = srec[j * (unsigned)V + v];
-                r[4 * v] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
+                const float4 t = srec[(unsigned)j[u] * (unsigned)V + v];
+                r[u][4 * v] = t.x; r[u][4 * v + 1] = t.y; r[u][4 * v + 2] = t.z; r[u][4 * v + 3] = t.w;
             }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
             float disp[D];
             float d2 = 0.0f;
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-                disp[k] = me[k] - r[k];
+                disp[k] = me[k] - r[u][k];
                 d2 += disp[k] * disp[k];
             }
-            if (i < nvalid && d2 < ga.rad2) {
+            if (valid[u] && d2 < ga.rad2) {
                 const bool pos = d2 > 0.0f;
                 const float inv = fast_rsqrt(d2);
                 const float d = pos ? d2 * inv : 0.0f;
@@ -405,9 +365,10 @@ k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
 #pragma unroll
                     for (int c = 0; c < SG::C(l); ++c) {
                         // pair (i, j): U_l[i] . data_l[j]      pair (j, i): U_l[j] . data_l[i]
-                        A = fmaf(me[SG::u_off(l) + c], r[SG::data_off(l) + c], A);
-                        Bv = fmaf(r[SG::u_off(l) + c], me[SG::data_off(l) + c], Bv);
-                        if (sym) a_dd[SG::chan_off(l) + c] = fmaf(s[l], r[SG::u_off(l) + c], a_dd[SG::chan_off(l) + c]);
+                        A = fmaf(me[SG::u_off(l) + c], r[u][SG::data_off(l) + c], A);
+                        Bv = fmaf(r[u][SG::u_off(l) + c], me[SG::data_off(l) + c], Bv);
+                        if (sym)
+                            a_dd[SG::chan_off(l) + c] = fmaf(s[l], r[u][SG::u_off(l) + c], a_dd[SG::chan_off(l) + c]);
                     }
                     TA = fmaf(A, t[l], TA);
                     TB = fmaf(Bv, t[l], TB);
@@ -417,7 +378,7 @@ k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
 #pragma unroll
                     for (int k = 0; k < D; ++k) a_dl[k] = fmaf(T, disp[k], a_dl[k]);
                 } else {
-                    const size_t jo = (size_t)b * N + j;
+                    const size_t jo = (size_t)b * N + j[u];
 #pragma unroll
                     for (int k = 0; k < D; ++k) {
                         a_dl[k] = fmaf(TA, disp[k], a_dl[k]);
@@ -434,18 +395,14 @@ k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
                 }
             }
         }
-        if (__all_sync(0xffffffffu, ended)) break;
+    });
+    if (G > 1) {
 #pragma unroll
-        for (int i = 0; i < kEPL; ++i) {
-            e[i] = nxt[i];
-            nxt[i] = -1.0f;
+        for (int k = 0; k < D; ++k) a_dl[k] = group_sum<G>(a_dl[k]);
+        if (sym) {
+#pragma unroll
+            for (int i = 0; i < CT; ++i) a_dd[i] = group_sum<G>(a_dd[i]);
         }
-    }
-#pragma unroll
-    for (int k = 0; k < D; ++k) a_dl[k] = group_sum(a_dl[k]);
-    if (sym) {
-#pragma unroll
-        for (int i = 0; i < CT; ++i) a_dd[i] = group_sum(a_dd[i]);
     }
     if (active && sub == 0) {
         if (sym) {
@@ -545,7 +502,7 @@ static void run_fwd(const float* locs, const float* neighbors, const GroupArgs& 
 {
     const long long BN = (long long)B * N;
     k_group_pack<SG, false><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec);
-    k_group_fwd<SG><<<dim3(cdiv((long long)N * kG, kThreads), B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K);
+    k_group_fwd<SG><<<dim3(cdiv((long long)N * SPNB_GROUP_FWD_G, kThreads), B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K);
 }
 template <typename SG>
 static void run_bwd(const float* locs, const float* neighbors, const GroupArgs& ga, int B, int N, int K,
@@ -553,7 +510,7 @@ static void run_bwd(const float* locs, const float* neighbors, const GroupArgs& 
 {
     const long long BN = (long long)B * N;
     k_group_pack<SG, true><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec);
-    k_group_bwd<SG><<<dim3(cdiv((long long)N * kG, kThreads), B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K,
+    k_group_bwd<SG><<<dim3(cdiv((long long)N * SPNB_GROUP_BWD_G, kThreads), B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K,
                                                                                         dlocs, sym_flag);
 }
 

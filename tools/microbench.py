@@ -26,12 +26,13 @@ from smoothparticlenets_b200 import _native as nat  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="fwd1,fwd3,bwd1,bwd3,collide,search,reorder,gA_fwd,gA_fb,gB_fwd,gB_fb,gV_fwd")
+    ap.add_argument("--only", default="fwd1,fwd3,bwd1,bwd3,collide,search,reorder,gA_fwd,gA_fb,gB_fwd,gB_fb,gV_fwd,gC_fwd,gC_fb")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--scenes", type=int, default=8)
     ap.add_argument("--particles", type=int, default=65536)
     ap.add_argument("--kernel", default="dspiky")
     ap.add_argument("--nosym", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="time a CUDA-graph replay (no CPU launch overhead)")
     args = ap.parse_args()
     only = set(args.only.split(","))
     B, N, D, R, K = args.scenes, args.particles, 3, 0.1, 128
@@ -47,7 +48,6 @@ def main():
     pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pp):
         peak = json.load(open(pp))["hbm_gbs"]
-    st = nat.stream()
     ones = torch.ones(B, N, 1, device="cuda")
     go1, go3 = torch.rand(B, N, 1, device="cuda"), torch.rand(B, N, 3, device="cuda")
     l1 = getattr(model, args.kernel + "1" + ("normd" if args.kernel in ("dspiky", "cohesion") else ""))
@@ -58,7 +58,7 @@ def main():
         return lambda: L.spnb_convsp_forward(
             nat.ptr(sl), nat.ptr(sl), nat.ptr(data), nat.ptr(nb), nat.ptr(layer.weight), nat.ptr(layer.bias),
             B, N, N, data.shape[2], D, K, O, 1, R, nat.ptr(layer.kernel_size), nat.ptr(layer.dilation),
-            layer.dis_norm, layer.kernel_fn, nat.ptr(out), st)
+            layer.dis_norm, layer.kernel_fn, nat.ptr(out), nat.stream())
 
     def bwd(layer, data, go):
         dl, dd = torch.empty_like(sl), torch.empty_like(data)
@@ -66,7 +66,7 @@ def main():
             nat.ptr(sl), nat.ptr(sl), nat.ptr(data), nat.ptr(nb), nat.ptr(layer.weight), B, N, N,
             data.shape[2], D, K, go.shape[2], 1, R, nat.ptr(layer.kernel_size), nat.ptr(layer.dilation),
             layer.dis_norm, layer.kernel_fn, nat.ptr(go), nat.ptr(dl), nat.ptr(dl), nat.ptr(dd), None,
-            nat.ptr(flag), None, st)
+            nat.ptr(flag), None, nat.stream())
 
     def search():
         with torch.no_grad():
@@ -79,12 +79,12 @@ def main():
     def collide():
         L.spnb_compute_collisions(nat.ptr(sl), nat.ptr(sl), nat.ptr(low), nat.ptr(gd), nat.ptr(model.coll.cellIDs),
                                   nat.ptr(model.coll.cellStarts), nat.ptr(model.coll.cellEnds), nat.ptr(coll_out),
-                                  B, N, N, D, K, 96 ** 3, R, R, 0, nat.ptr(tflag), st)
+                                  B, N, N, D, K, 96 ** 3, R, R, 0, nat.ptr(tflag), nat.stream())
 
     ro_l, ro_v = torch.empty_like(locs), torch.empty_like(vel)
 
     def reorder():
-        L.spnb_reorder_data(nat.ptr(locs), nat.ptr(vel), nat.ptr(idxs), nat.ptr(ro_l), nat.ptr(ro_v), B, N, D, 3, 0, st)
+        L.spnb_reorder_data(nat.ptr(locs), nat.ptr(vel), nat.ptr(idxs), nat.ptr(ro_l), nat.ptr(ro_v), B, N, D, 3, 0, nat.stream())
 
     # fused groups (ConvSPGroup) of the fluid step: forward and forward+backward through autograd
     model_f = fluidstep.FluidStep(spn, radius=R, max_collisions=K, fused=True).cuda()
@@ -109,6 +109,7 @@ def main():
     mkA = lambda l: [ones, l, ones, l, ones, ones]
     mkB = lambda l: [l * press, press]
     mkV = lambda l: [sv, ones]
+    mkC = lambda l: [sv]
 
     P = B * N
     fb = lambda C, O: 4 * D + 4 * C + 4 * (nbar + 1) + 4 * O
@@ -124,6 +125,8 @@ def main():
         "gB_fwd": (group_fwd(model_f.group_b, mkB), P * (fb(1, 1) + fb(3, 3))),
         "gB_fb": (group_fb(model_f.group_b, mkB), P * (fb(1, 1) + bb(1, 1) + fb(3, 3) + bb(3, 3))),
         "gV_fwd": (group_fwd(model_f.group_v, mkV), P * (fb(1, 1) + fb(3, 3))),
+        "gC_fwd": (group_fwd(model_f.group_c, mkC), P * fb(3, 3)),
+        "gC_fb": (group_fb(model_f.group_c, mkC), P * (fb(3, 3) + bb(3, 3))),
     }
     print("nbar %.2f  peak %.0f GB/s" % (nbar, peak))
     for name, (fn, byts) in table.items():
@@ -133,10 +136,26 @@ def main():
             fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        e0.record()
-        for _ in range(args.iters):
-            fn()
-        e1.record()
+        if args.graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for _ in range(args.iters):
+                    fn()
+            gr.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            gr.replay()
+            e1.record()
+        else:
+            e0.record()
+            for _ in range(args.iters):
+                fn()
+            e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.iters
         gbs = byts / (ms * 1e-3) / 1e9
