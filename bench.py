@@ -164,8 +164,6 @@ def time_kernels(torch, spn, model, locs, vel, iters=10):
     flag = nb._spnb_sym_flag
     ones = torch.ones(B, N, 1, device="cuda")
     go1, go3 = torch.rand(B, N, 1, device="cuda"), torch.rand(B, N, 3, device="cuda")
-    st = nat.stream()
-
     def ev_time(fn):
         for _ in range(3):
             fn()
@@ -183,7 +181,7 @@ def time_kernels(torch, spn, model, locs, vel, iters=10):
         return lambda: L.spnb_convsp_forward(
             nat.ptr(sl), nat.ptr(sl), nat.ptr(data), nat.ptr(nb), nat.ptr(layer.weight), nat.ptr(layer.bias),
             B, N, N, data.shape[2], D, nb.shape[2], O, 1, float(RADIUS), nat.ptr(layer.kernel_size),
-            nat.ptr(layer.dilation), layer.dis_norm, layer.kernel_fn, nat.ptr(out), st)
+            nat.ptr(layer.dilation), layer.dis_norm, layer.kernel_fn, nat.ptr(out), nat.stream())
 
     def bwd(layer, data, go):
         dl, dd = torch.empty_like(sl), torch.empty_like(data)
@@ -191,7 +189,7 @@ def time_kernels(torch, spn, model, locs, vel, iters=10):
             nat.ptr(sl), nat.ptr(sl), nat.ptr(data), nat.ptr(nb), nat.ptr(layer.weight), B, N, N,
             data.shape[2], D, nb.shape[2], go.shape[2], 1, float(RADIUS), nat.ptr(layer.kernel_size),
             nat.ptr(layer.dilation), layer.dis_norm, layer.kernel_fn, nat.ptr(go), nat.ptr(dl), nat.ptr(dl),
-            nat.ptr(dd), None, nat.ptr(flag), None, st)
+            nat.ptr(dd), None, nat.ptr(flag), None, nat.stream())
 
     P = B * N
     fb = lambda C, O: 4 * D + 4 * C + 4 * (nbar + 1) + 4 * O
@@ -208,7 +206,52 @@ def time_kernels(torch, spn, model, locs, vel, iters=10):
             model.coll(locs, vel)
     # whole neighbour-search chain (bounds, sort, reorder, table, lists): 12+20+52+528 B/particle
     res["particle_collision"] = (ev_time(collide), 1, P * (4 * D + (4 * D + 8) + (4 + 8 * (D + D)) + (4 * D + 4 + 4 * K_NEIGH)))
-    return res, nbar
+    if not getattr(model, "fused", False):
+        return res, nbar, {}
+
+    # ---- fused groups: one op = pack pre-pass + one walk over the lists (C ABI called directly)
+    from smoothparticlenets_b200 import convsp_group as cg
+    press = torch.rand(B, N, 1, device="cuda")
+    groups = {
+        "A": (model.group_a, [ones, sl, ones, sl, ones, ones], 3),
+        "B": (model.group_b, [sl * press, press], 3),
+        "C": (model.group_c, [sv], 3),
+        "V": (model.group_v, [sv, ones], 1),
+    }
+    fused, reduced = {}, {}
+    for name, (grp, datas, per_step) in groups.items():
+        layers = list(grp.layers)
+        cfg = tuple((l.kernel_fn, l.dis_norm, l.nchannels, l.nkernels) for l in layers)
+        ws_ = [l.weight for l in layers]
+        bs_ = [l.bias for l in layers]
+        outs = [torch.empty(B, N, c[3], device="cuda") for c in cfg]
+        gos = [torch.rand(B, N, c[3], device="cuda") for c in cfg]
+        dds = [torch.empty_like(d) if d is not ones else None for d in datas]
+        dl = torch.empty_like(sl)
+        afw = cg._layer_array(sl, datas, ws_, bs_, cfg, outs=outs)
+        abw = cg._layer_array(sl, datas, ws_, None, cfg, gos=gos, ddatas=dds)
+        wf = L.spnb_convsp_group_workspace_bytes(nat.ptr(sl), B, N, D, float(RADIUS), len(cfg), afw, 0)
+        wb = L.spnb_convsp_group_workspace_bytes(nat.ptr(sl), B, N, D, float(RADIUS), len(cfg), abw, 1)
+        wsf = torch.empty(wf // 4 + 1, device="cuda")
+        wsb = torch.empty(wb // 4 + 1, device="cuda")
+        f_fn = lambda afw=afw, wsf=wsf, wf=wf, n=len(cfg): L.spnb_convsp_group_forward(
+            nat.ptr(sl), nat.ptr(nb), B, N, D, nb.shape[2], float(RADIUS), n, afw, nat.ptr(wsf), wf, nat.stream())
+        b_fn = lambda abw=abw, wsb=wsb, wb=wb, n=len(cfg), dl=dl: L.spnb_convsp_group_backward(
+            nat.ptr(sl), nat.ptr(nb), B, N, D, nb.shape[2], float(RADIUS), n, abw, nat.ptr(dl), nat.ptr(flag),
+            nat.ptr(wsb), wb, nat.stream())
+        # SURVEY 8(d) bytes of the layers this op replaces, and the op's own compulsory bytes
+        eq_f = sum(fb(c[2], c[3]) for c in cfg)
+        eq_b = sum(bb(c[2], c[3]) for c in cfg)
+        distinct = {id(d): d.shape[2] for d in datas if d is not sl}
+        ch_out = sum(c[3] for c in cfg)
+        own_f = 4 * D + 4 * (nbar + 1) + 4 * sum(distinct.values()) + 4 * ch_out
+        own_b = own_f + 4 * D + sum(4 * d.shape[2] for d, g_ in zip(datas, dds) if g_ is not None)
+        fused["group%s_fwd" % name] = (ev_time(f_fn), per_step, P * eq_f)
+        fused["group%s_bwd" % name] = (ev_time(b_fn), per_step, P * eq_b)
+        reduced["group%s_fwd" % name] = P * own_f
+        reduced["group%s_bwd" % name] = P * own_b
+    fused["particle_collision"] = res["particle_collision"]
+    return fused, nbar, reduced
 
 
 # ------------------------------------------------------------------------------------------------
@@ -241,7 +284,8 @@ def run_ours(args):
     locs_pin = torch.from_numpy(locs_h).pin_memory()
     vel_pin = torch.from_numpy(vel_h).pin_memory()
     locs, vel = locs_pin.cuda(), vel_pin.cuda()
-    model = fluidstep.FluidStep(spn, radius=RADIUS, max_collisions=K_NEIGH, fused=args.fused).cuda()
+    fused = not args.layerwise
+    model = fluidstep.FluidStep(spn, radius=RADIUS, max_collisions=K_NEIGH, fused=fused).cuda()
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
     grad_outs = [torch.rand(B, N, 3, device="cuda", generator=g) for _ in range(2)]
 
@@ -310,17 +354,32 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms_eager = 1e3 * (time.perf_counter() - t0) / 3
 
+    # ---- the same step through the per-layer drop-in modules (reported beside the headline)
+    ms_alt = None
+    if fused:
+        alt = fluidstep.FluidStep(spn, radius=RADIUS, max_collisions=K_NEIGH, fused=False).cuda()
+        alt_step = GraphedStep(lambda l, v: alt(l, v), [locs, vel], grad_outs, warmup=3)
+        alt_step.replay()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            alt_step.replay()
+        e1.record()
+        barrier()
+        ms_alt = e0.elapsed_time(e1)
+
     if dist is not None:
-        t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_alt or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+        ms_alt = float(t[2]) if ms_alt is not None else None
 
     total_particles = world * B * N
     value = total_particles * args.steps / (ms * 1e-3)
     e2e_value = total_particles * args.steps / (ms_e2e * 1e-3)
 
     if rank == 0:
-        kern, nbar = time_kernels(torch, spn, model, locs, vel)
+        kern, nbar, reduced = time_kernels(torch, spn, model, locs, vel)
         peaks = {}
         ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(ppath):
@@ -337,7 +396,8 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(B, N), "scenes_per_gpu": B, "particles_per_scene": N,
                        "nbar": round(nbar, 2), "execution": "one CUDA graph per fwd+bwd step",
-                       "convsp_path": "ConvSPGroup (fused per dependency phase)" if args.fused else "per-layer drop-in modules",
+                       "convsp_path": ("ConvSPGroup: layers sharing (locs, neighbors) fused per dependency phase"
+                                       if fused else "per-layer drop-in modules"),
                        "l2": "inputs larger than L2 (neighbour lists alone are %d MB per GPU)" % (B * N * K_NEIGH * 4 >> 20),
                        "outputs_finite": finite},
             "clocks": clk,
@@ -347,7 +407,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": byts, "ms_per_launch": t_ms,
-                         "share_of_step": shares[top] / sum(shares.values())},
+                         "share_of_step": shares[top] / sum(shares.values()),
+                         "bytes_definition": ("SURVEY.md 8(d) per-layer bytes summed over the layers the fused op "
+                                              "replaces (pack pre-pass + list walk timed together)" if fused else
+                                              "SURVEY.md 8(d) per-layer bytes"),
+                         "achieved_own_bytes": (reduced[top] / (t_ms * 1e-3) / 1e9) if top in reduced else None},
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes,
                               "achieved_gbs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                               "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
@@ -355,6 +419,10 @@ def run_ours(args):
                         for k, v in kern.items()},
             "eager_ms_per_step": ms_eager,
         }
+        if ms_alt is not None:
+            line["per_layer"] = {"value": total_particles * args.steps / (ms_alt * 1e-3), "unit": UNIT,
+                                 "ms_per_step": ms_alt / args.steps,
+                                 "note": "same step through the drop-in per-layer ConvSP modules (no ConvSPGroup)"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_particles)
         print(json.dumps(line))
@@ -373,8 +441,8 @@ def main():
     ap.add_argument("--particles", type=int, default=PARTICLES)
     ap.add_argument("--cpu-particles", type=int, default=CPU_SAMPLE_PARTICLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fused", action="store_true",
-                    help="evaluate layers that share (locs, neighbors) through ConvSPGroup (opt-in extension)")
+    ap.add_argument("--layerwise", action="store_true",
+                    help="headline through the per-layer drop-in modules instead of ConvSPGroup")
     args = ap.parse_args()
     if args.impl == "reference":
         # bounded sample: each step is one 8192-particle scene per host core (~2.5 s)
