@@ -277,6 +277,9 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO level
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     B, N = args.scenes, args.particles
