@@ -249,8 +249,16 @@ k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
 #pragma unroll
     for (int i = 0; i < CT; ++i) G_[i] = 0.0f;
     const float* warp_rows = neighbors + ((size_t)b * N + min(m0, N - 1)) * K;
+    prefetch_rows_ahead(neighbors, N, K, QPB, 2);
 
     walk_rows<G, kU>(warp_rows, K, nrows, s_walk[warp], [&](const int* j, const bool* valid) {
+#if defined(SPNB_DEBUG_WALK_ONLY)
+        // experiment: list walk without gathers or math (measures the row-staging floor)
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+            if (valid[u]) G_[0] += (float)j[u];
+        return;
+#endif
         float r[kU][V * 4];
 #pragma unroll
         for (int u = 0; u < kU; ++u)
@@ -259,6 +267,13 @@ k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
                 const float4 t = srec[(unsigned)j[u] * (unsigned)V + v];
                 r[u][4 * v] = t.x; r[u][4 * v + 1] = t.y; r[u][4 * v + 2] = t.z; r[u][4 * v + 3] = t.w;
             }
+#if defined(SPNB_DEBUG_NO_MATH)
+        // experiment: gathers without the pair math (measures the gather floor)
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+            if (valid[u]) G_[0] += r[u][0] + r[u][V * 4 - 1];
+        return;
+#endif
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
             float d2 = 0.0f;
@@ -333,6 +348,7 @@ k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
 #pragma unroll
     for (int i = 0; i < CT; ++i) a_dd[i] = 0.0f;
     const float* warp_rows = neighbors + ((size_t)b * N + min(m0, N - 1)) * K;
+    prefetch_rows_ahead(neighbors, N, K, QPB, 2);
 
     walk_rows<G, UB>(warp_rows, K, nrows, s_walk[warp], [&](const int* j, const bool* valid) {
         float r[UB][V * 4];

@@ -103,6 +103,7 @@ k_convsp_fwd_small(const float* __restrict__ qlocs, const float* __restrict__ lo
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.0f;
     const float* warp_rows = neighbors + ((size_t)b * M + min(m0, M - 1)) * K;
+    prefetch_rows_ahead(neighbors, M, K, QPB, 2);
 
     walk_rows<G, U>(warp_rows, K, nrows, s_walk[warp], [&](const int* j, const bool* valid) {
         float y[U][D], dj[U][C];
@@ -201,6 +202,7 @@ k_convsp_bwd_small(const float* __restrict__ qlocs, const float* __restrict__ lo
 #pragma unroll
     for (int i = 0; i < (WDW ? O * C : 1); ++i) a_dw[i] = 0.0f;
     const float* warp_rows = neighbors + ((size_t)b * M + min(m0, M - 1)) * K;
+    prefetch_rows_ahead(neighbors, M, K, QPB, 2);
 
     walk_rows<G, U>(warp_rows, K, nrows, s_walk[warp], [&](const int* j, const bool* valid) {
         float y[U][D], dj[U][C], gj[U][O];

@@ -1,10 +1,10 @@
 // Neighbour-list walker shared by the ConvSP kernels (convsp_small.cu, convsp_group.cu).
 //
 // G lanes cooperate on one query (G = 1, 2, 4 or 8; R = 32/G queries per warp).  The rows of the
-// warp's queries are staged 32 entries at a time through shared memory: for each row the warp reads
-// one coalesced 128-byte segment, and the same pass finds the row's terminator with ONE ballot (the
-// list ends at the first negative entry, common_funcs.h:476), so the inner loop needs no per-entry
-// termination logic.  Lane `sub` of a group then consumes entries sub, sub+G, ... of its row, U at a
+// warp's queries are staged 32 entries (128 bytes) at a time in shared memory and the row's
+// terminator (the list ends at the first negative entry, common_funcs.h:476) is located once per
+// chunk, so the inner loop needs no per-entry termination logic.  Lane `sub` of a group then
+// consumes entries sub, sub+G, ... of its row, U at a
 // time, which gives U independent gathers in flight per lane; the G lanes of a group touch G
 // consecutive list entries, i.e. (the lists being in cell order) mostly consecutive particles.
 //
@@ -25,50 +25,71 @@ struct WalkSmem {
     int cnt[R];
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // warp_rows: row of the warp's first query (rows are K floats apart).  nrows: how many of the warp's
 // R queries exist.  body(const int* j, const bool* valid) is called with U list entries of this
 // lane's query (valid[u] == false: no entry).
+//
+// Staging: when rows are 16-byte aligned and the chunk lies inside the row, every group copies ITS OWN
+// row chunk with cp.async (LDGSTS, 16 bytes per lane and instruction, no register round trip); the
+// terminator is then found by the group itself: each lane scans the 32/G entries it is going to
+// consume anyway and the group takes the minimum with log2(G) shuffles.  Otherwise (ragged K,
+// unaligned base) the warp stages row by row with one ballot per row.
 template <int G, int U, typename Body>
 __device__ __forceinline__ void walk_rows(const float* __restrict__ warp_rows, int K, int nrows,
                                           WalkSmem<G>& sm, Body body)
 {
-    constexpr int R = WalkSmem<G>::R, STRIDE = WalkSmem<G>::STRIDE;
+    constexpr int R = WalkSmem<G>::R, STRIDE = WalkSmem<G>::STRIDE, EPL = 32 / G;
     const int lane = threadIdx.x & 31;
     const int g = lane / G, sub = lane % G;
-    unsigned live = nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u);  // rows still walking
-    for (int base = 0; base < K && live; base += 32) {
-        const unsigned start_live = live;
-        const int p = base + lane;
+    const bool aligned = ((K & 3) == 0) && ((reinterpret_cast<size_t>(warp_rows) & 15) == 0);
+    bool mine = g < nrows;  // my group's row is still being walked
+    for (int base = 0; base < K; base += 32) {
+        if (!__any_sync(0xffffffffu, mine)) break;
         __syncwarp();  // the previous chunk has been consumed by every lane
-        if (start_live == (R >= 32 ? 0xffffffffu : ((1u << R) - 1u))) {
-            // all rows: batches of 8 independent loads
+        int cnt = 0;
+        if (aligned && base + 32 <= K) {
+            if (mine) {
+                const float* src = warp_rows + (size_t)g * K + base;
 #pragma unroll
-            for (int r0 = 0; r0 < R; r0 += 8) {
-                float f[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (r0 + i < R) f[i] = p < K ? warp_rows[(size_t)(r0 + i) * K + p] : -1.0f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (r0 + i < R) {
-                        sm.nb[(r0 + i) * STRIDE + lane] = f[i];
-                        const unsigned neg = __ballot_sync(0xffffffffu, !(f[i] >= 0.0f));
-                        if (lane == 0) sm.cnt[r0 + i] = neg ? __ffs(neg) - 1 : 32;
-                        if (neg) live &= ~(1u << (r0 + i));
-                    }
+                for (int i = 0; i < 8 / G; ++i)  // 128 bytes per row chunk, 16 bytes per lane and copy
+                    cp_async16(&sm.nb[g * STRIDE + (sub + i * G) * 4], src + (sub + i * G) * 4);
             }
+            cp_async_wait_all();
+            __syncwarp();
+            // first negative entry among mine (positions sub, sub+G, ...), then over the group
+            int first = 32;
+            if (mine) {
+#pragma unroll
+                for (int i = EPL - 1; i >= 0; --i)
+                    if (!(sm.nb[g * STRIDE + sub + i * G] >= 0.0f)) first = sub + i * G;
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            cnt = mine ? first : 0;
         } else {
-            for (unsigned m = start_live; m; m &= m - 1) {
-                const int r = __ffs(m) - 1;
+            const unsigned live = __ballot_sync(0xffffffffu, mine && sub == 0);
+            const int p = base + lane;
+            for (unsigned m = live; m; m &= m - 1) {
+                const int r = (__ffs(m) - 1) / G;
                 const float f = p < K ? warp_rows[(size_t)r * K + p] : -1.0f;
                 sm.nb[r * STRIDE + lane] = f;
                 const unsigned neg = __ballot_sync(0xffffffffu, !(f >= 0.0f));
                 if (lane == 0) sm.cnt[r] = neg ? __ffs(neg) - 1 : 32;
-                if (neg) live &= ~(1u << r);
             }
+            __syncwarp();
+            cnt = mine ? sm.cnt[g] : 0;
         }
-        __syncwarp();
-        const int cnt = ((start_live >> g) & 1u) ? sm.cnt[g] : 0;
+        if (cnt < 32) mine = false;  // terminator seen (or no row): nothing after this chunk
         for (int t0 = sub; t0 < 32; t0 += G * U) {
             if (!__any_sync(0xffffffffu, t0 < cnt)) break;
             int j[U];
@@ -82,6 +103,31 @@ __device__ __forceinline__ void walk_rows(const float* __restrict__ warp_rows, i
             body(j, valid);
         }
     }
+}
+
+// L2 prefetch of the neighbour rows that a LATER block will walk.  The walk is latency-bound on the
+// first touch of each row (measured: a walk with no gathers and no math already costs ~60 us at c2,
+// 4x the DRAM time of the bytes it reads), because a warp alternates between waiting for its rows
+// and consuming them.  Blocks are dispatched in linear order, so a block asks L2 for the rows of the
+// block that will run roughly one "wave of resident blocks" later; by then they are L2 hits.
+// rows_per_block queries per block, `lines` 128-byte lines per row are prefetched.
+#ifndef SPNB_PREFETCH_BLOCKS
+#define SPNB_PREFETCH_BLOCKS (148 * 16)
+#endif
+__device__ __forceinline__ void prefetch_rows_ahead(const float* __restrict__ neighbors, int M, int K,
+                                                    int rows_per_block, int lines)
+{
+    const long long nblocks = (long long)gridDim.x * gridDim.y;
+    const long long lb = (long long)blockIdx.y * gridDim.x + blockIdx.x + SPNB_PREFETCH_BLOCKS;
+    if (lb >= nblocks) return;
+    const int b2 = (int)(lb / gridDim.x), x2 = (int)(lb % gridDim.x);
+    const int t = threadIdx.x;
+    const int row = t / lines, line = t % lines;
+    if (row >= rows_per_block) return;
+    const int m = x2 * rows_per_block + row;
+    if (m >= M || line * 32 >= K) return;
+    const float* p = neighbors + ((size_t)b2 * M + m) * K + line * 32;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // Sum over the G lanes of a group (all lanes receive the total).
