@@ -167,8 +167,8 @@ k_convsp_fwd_generic(const float* __restrict__ qlocs, const float* __restrict__ 
     }
 }
 
-// Generic backward: dq by group reduction, everything neighbour-side and dweight by float atomics
-// into zero-filled buffers (the launcher zero-fills).  `out` rows hold grad_output.
+// Generic backward: dq by group reduction, everything neighbour-side by float atomics into
+// zero-filled buffers (the launcher zero-fills); d(weight) is k_convsp_dweight_generic below.
 template <int DT>
 __global__ void __launch_bounds__(kThreads)
 k_convsp_bwd_generic(const float* __restrict__ qlocs, const float* __restrict__ locs,
@@ -181,15 +181,10 @@ k_convsp_bwd_generic(const float* __restrict__ qlocs, const float* __restrict__ 
 {
     constexpr int MD = DT > 0 ? DT : SPNB_MAXD;
     const int D = DT > 0 ? DT : ndims;
-    extern __shared__ float s_mem[];  // [weights][dweight accumulators] when w_in_smem
-    float* s_w = s_mem;
-    float* s_dw = s_mem + (size_t)O * C * ncells;
+    extern __shared__ float s_w[];  // weights when w_in_smem
     const int nw = O * C * ncells;
     if (w_in_smem) {
-        for (int i = threadIdx.x; i < nw; i += kThreads) {
-            s_w[i] = weight[i];
-            s_dw[i] = 0.0f;
-        }
+        for (int i = threadIdx.x; i < nw; i += kThreads) s_w[i] = weight[i];
         __syncthreads();
     }
     const float* wp = w_in_smem ? s_w : weight;
@@ -258,11 +253,6 @@ k_convsp_bwd_generic(const float* __restrict__ qlocs, const float* __restrict__ 
                                 const float wv = wp[wi];
                                 const float g = gi[o];
                                 v_dd += g * wv * kw * norm;
-                                if (dw) {
-                                    const float v = g * dv * kw * norm;
-                                    if (w_in_smem) atomicAdd(&s_dw[wi], v);
-                                    else atomicAdd(dw + wi, v);
-                                }
                                 if (d > 0.0f) {
 #pragma unroll
                                     for (int k = 0; k < D; ++k) {
@@ -299,10 +289,107 @@ k_convsp_bwd_generic(const float* __restrict__ qlocs, const float* __restrict__ 
             else dq[q * D + k] = a_dq[k];
         }
     }
-    if (dw && w_in_smem) {
+}
+
+// d(weight) for the generic path, in a kernel of its own so that the whole warp stays convergent:
+// every lane walks the kernel cells in lockstep, per cell the data[j,c]*W*norm terms of a query's
+// lanes are summed with shuffles and one lane per query adds go[q,o] times that sum to the block's
+// shared accumulator (the reference does one global atomicAdd per term, all threads on the same
+// nkernels*nchannels*ncells addresses, common_funcs.h:542-547).
+template <int DT>
+__global__ void __launch_bounds__(kThreads)
+k_convsp_dweight_generic(const float* __restrict__ qlocs, const float* __restrict__ locs,
+                         const float* __restrict__ data, const float* __restrict__ neighbors,
+                         const float* __restrict__ go, long long BM, int M, int N, int C, int ndims, int K,
+                         int O, int ncells, float radius, const float* __restrict__ ksize,
+                         const float* __restrict__ dilation, int dis_norm, SphParams sp, float* dw,
+                         int acc_in_smem)
+{
+    constexpr int MD = DT > 0 ? DT : SPNB_MAXD;
+    const int D = DT > 0 ? DT : ndims;
+    extern __shared__ float s_acc[];
+    const int nw = O * C * ncells;
+    if (acc_in_smem) {
+        for (int i = threadIdx.x; i < nw; i += kThreads) s_acc[i] = 0.0f;
+        __syncthreads();
+    }
+    float* acc = acc_in_smem ? s_acc : dw;
+    const int lane = threadIdx.x & 31, sub = lane & (kG - 1);
+    const long long q = ((long long)blockIdx.x * kThreads + threadIdx.x) / kG;
+    const bool active = q < BM;
+    const long long qq = active ? q : 0;
+    const int b = (int)(qq / M);
+    int ks[MD], half[MD];
+    float dil[MD], x[MD], cull2;
+    load_shape<DT>(ksize, dilation, D, radius, ks, half, dil, cull2);
+    const float rad2 = radius * radius;
+#pragma unroll
+    for (int k = 0; k < D; ++k) x[k] = qlocs[qq * D + k];
+    const float* row = neighbors + qq * K;
+    const float* sl = locs + (size_t)b * N * D;
+    const float* sd = data + (size_t)b * N * C;
+    const float* gi = go + qq * O;
+
+    for (int jj0 = 0; jj0 < K; jj0 += kG) {
+        const int jj = jj0 + sub;
+        const float nb = (active && jj < K) ? row[jj] : -1.0f;
+        const unsigned neg = __ballot_sync(0xffffffffu, !(nb >= 0.0f));
+        const int fneg = group_first_neg(neg, lane, sub);
+        bool live = sub < fneg;
+        const int j = live ? (int)nb : 0;
+        const float* dj = sd + (size_t)j * C;
+        float yy[MD];
+        float d0 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            yy[k] = sl[(size_t)j * D + k];
+            d0 += (x[k] - yy[k]) * (x[k] - yy[k]);
+        }
+        if (d0 > cull2) live = false;
+        if (__any_sync(0xffffffffu, live)) {
+            int kidx[MD];
+#pragma unroll
+            for (int k = 0; k < D; ++k) kidx[k] = 0;
+            for (int cell = 0; cell < ncells; ++cell) {
+                float d = 0.0f;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    const float nr = x[k] + (kidx[k] - half[k]) * dil[k] - yy[k];
+                    d += nr * nr;
+                }
+                float s = 0.0f;
+                if (live && d < rad2) {
+                    d = sqrtf(d);
+                    float norm = 1.0f;
+                    if (dis_norm && d > 0.0f) norm /= d;
+                    s = (d > sp.H ? 0.0f : sph_eval(sp.w_expr, d, sp.H, sp.w_coef)) * norm;
+                }
+                if (__any_sync(0xffffffffu, s != 0.0f)) {
+                    // the lanes of a group share the query, hence go[q,:]: reduce data*W*norm over the
+                    // group first, then one lane per group applies go and adds O values per channel
+                    for (int c = 0; c < C; ++c) {
+                        float tc = s != 0.0f ? dj[c] * s : 0.0f;
+                        tc = group_sum(tc);
+                        if (sub == 0 && tc != 0.0f)
+                            for (int o = 0; o < O; ++o)
+                                atomicAdd(acc + ((size_t)o * C + c) * ncells + cell, gi[o] * tc);
+                    }
+                }
+                ++kidx[0];
+#pragma unroll
+                for (int k = 0; k < D - 1; ++k)
+                    if (kidx[k] >= ks[k]) {
+                        kidx[k] = 0;
+                        ++kidx[k + 1];
+                    }
+            }
+        }
+        if (__all_sync(0xffffffffu, fneg < kG)) break;
+    }
+    if (acc_in_smem) {
         __syncthreads();
         for (int i = threadIdx.x; i < nw; i += kThreads) {
-            const float v = s_dw[i];
+            const float v = s_acc[i];
             if (v != 0.0f) atomicAdd(dw + i, v);
         }
     }
@@ -421,8 +508,8 @@ int spnb_convsp_backward(const float* qlocs, const float* locs, const float* dat
                                 same, stream);
     } else {
         const size_t wbytes = sizeof(float) * (size_t)O * C * ncells;
-        const int ws = 2 * wbytes <= (size_t)(2 * kMaxSmemWeights);
-        const size_t smem = ws ? 2 * wbytes : 0;
+        const int ws = wbytes <= (size_t)kMaxSmemWeights;
+        const size_t smem = ws ? wbytes : 0;
 #define LAUNCH(DT)                                                                                 \
     do {                                                                                           \
         if (smem > 48 * 1024)                                                                      \
@@ -439,6 +526,27 @@ int spnb_convsp_backward(const float* qlocs, const float* locs, const float* dat
         default: LAUNCH(0); break;
         }
 #undef LAUNCH
+        if (dweight) {
+            const int as = wbytes <= (size_t)(96 * 1024);
+            const size_t asmem = as ? wbytes : 0;
+#define LAUNCHW(DT)                                                                                \
+    do {                                                                                           \
+        if (asmem > 48 * 1024)                                                                     \
+            cudaFuncSetAttribute(k_convsp_dweight_generic<DT>,                                     \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem);         \
+        k_convsp_dweight_generic<DT><<<blocks, kThreads, asmem, stream>>>(                         \
+            qlocs, locs, data, neighbors, grad_out, BM, M, N, C, D, K, O, ncells, radius,          \
+            kernel_size, dilation, dis_norm, sp, dweight, as);                                     \
+    } while (0)
+            switch (D) {
+            case 1: LAUNCHW(1); break;
+            case 2: LAUNCHW(2); break;
+            case 3: LAUNCHW(3); break;
+            default: LAUNCHW(0); break;
+            }
+#undef LAUNCHW
+            count_launches(1);
+        }
     }
     count_launches(1);
     return check_launch("spnb_convsp_backward") ? 1 : 0;
