@@ -96,6 +96,19 @@ int spnb_convsp_forward(const float* qlocs, const float* locs, const float* data
                         int nkernels, int ncells, float radius, const float* kernel_size,
                         const float* dilation, int dis_norm, int kernel_fn, float* out, void* stream);
 
+/* Forward for wide channel counts (nchannels >= 32, nkernels <= 256, ndims <= 3; BASELINE.json config
+ * 3): same result as spnb_convsp_forward, computed in the factored form
+ *   G[q,cell,c] = sum_j W*norm*data[j,c],  out[q,o] = bias[o] + sum_{cell,c} weight[o,c,cell]*G[q,cell,c]
+ * with the weights transposed into `workspace` (spnb_convsp_forward_wide_workspace_bytes() bytes, 0 =
+ * shape not supported: use spnb_convsp_forward). */
+size_t spnb_convsp_forward_wide_workspace_bytes(int nkernels, int nchannels, int ndims, int ncells);
+int spnb_convsp_forward_wide(const float* qlocs, const float* locs, const float* data,
+                             const float* neighbors, const float* weight, const float* bias,
+                             int batch_size, int M, int N, int nchannels, int ndims, int max_neighbors,
+                             int nkernels, int ncells, float radius, const float* kernel_size,
+                             const float* dilation, int dis_norm, int kernel_fn, float* out,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* Backward.  Replaces cuda_convsp with non-NULL gradients.  Any of dqlocs/dlocs/ddata/dweight may be
  * NULL (not computed).  sym_flag: optional device int; when non-NULL, qlocs == locs, and *sym_flag
  * == 0 at execution time, the neighbour relation is taken to be symmetric and dlocs/ddata are

@@ -25,6 +25,8 @@ _SIGNATURES = {
     "spnb_compute_collisions": (_i, [_vp] * 8 + [_i] * 6 + [_f, _f, _i, _vp, _vp]),
     "spnb_reorder_data": (_i, [_vp] * 5 + [_i] * 5 + [_vp]),
     "spnb_convsp_forward": (_i, [_vp] * 6 + [_i] * 8 + [_f, _vp, _vp, _i, _i, _vp, _vp]),
+    "spnb_convsp_forward_wide_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "spnb_convsp_forward_wide": (_i, [_vp] * 6 + [_i] * 8 + [_f, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "spnb_convsp_backward_workspace_bytes": (_sz, [_i, _i, _i]),
     "spnb_convsp_backward": (_i, [_vp] * 5 + [_i] * 8 + [_f, _vp, _vp, _i, _i] + [_vp] * 8),
     "spnb_convsp_group_workspace_bytes": (_sz, [_vp, _i, _i, _i, _f, _i, _vp, _i]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB_PATH = os.path.join(HERE, "libspnb.so")
-SOURCES = ["common.cu", "hashgrid.cu", "convsp.cu", "convsp_small.cu", "convsp_group.cu", "convsdf.cu"]
+SOURCES = ["common.cu", "hashgrid.cu", "convsp.cu", "convsp_small.cu", "convsp_group.cu", "convsp_wide.cu", "convsdf.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -101,12 +101,22 @@ class _ConvSPFunction(torch.autograd.Function):
             raise ValueError("neighbors must be %dx%dxK, not %s" % (B, M, tuple(neighbors.shape)))
         out = torch.empty(B, M, O, device=locs.device, dtype=torch.float32)
         L = nat.lib()
+        # wide channel counts: factored gather + dense contraction (csrc/convsp_wide.cu)
+        wide_bytes = L.spnb_convsp_forward_wide_workspace_bytes(O, C, D, ncells) if C * O * ncells >= 4096 else 0
         with torch.cuda.device(locs.device):
-            nat.check(L.spnb_convsp_forward(
-                nat.ptr(q), nat.ptr(locs), nat.ptr(data), nat.ptr(neighbors), nat.ptr(weight),
-                nat.ptr(bias), B, M, N, C, D, K, O, ncells, radius, nat.ptr(kernel_size),
-                nat.ptr(dilation), dis_norm, kernel_fn, nat.ptr(out), nat.stream()),
-                "spnb_convsp_forward")
+            if wide_bytes:
+                ws = torch.empty((wide_bytes + 3) // 4, device=locs.device, dtype=torch.float32)
+                nat.check(L.spnb_convsp_forward_wide(
+                    nat.ptr(q), nat.ptr(locs), nat.ptr(data), nat.ptr(neighbors), nat.ptr(weight),
+                    nat.ptr(bias), B, M, N, C, D, K, O, ncells, radius, nat.ptr(kernel_size),
+                    nat.ptr(dilation), dis_norm, kernel_fn, nat.ptr(out), nat.ptr(ws), wide_bytes,
+                    nat.stream()), "spnb_convsp_forward_wide")
+            else:
+                nat.check(L.spnb_convsp_forward(
+                    nat.ptr(q), nat.ptr(locs), nat.ptr(data), nat.ptr(neighbors), nat.ptr(weight),
+                    nat.ptr(bias), B, M, N, C, D, K, O, ncells, radius, nat.ptr(kernel_size),
+                    nat.ptr(dilation), dis_norm, kernel_fn, nat.ptr(out), nat.stream()),
+                    "spnb_convsp_forward")
         ctx.save_for_backward(qlocs, locs, data, neighbors, weight, kernel_size, dilation)
         ctx.cfg = (radius, dis_norm, kernel_fn, ncells)
         ctx.sym_flag = sym_flag

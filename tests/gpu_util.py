@@ -120,3 +120,18 @@ def convsp_backward(q, locs, data, nb, w, radius, ksize, dil, dis_norm, fn, go, 
                                      nat.ptr(dl), nat.ptr(dd), nat.ptr(dw), nat.ptr(sym_flag), None,
                                      nat.stream()), "convsp_backward")
     return dq, dl, dd, dw
+
+
+def convsp_forward_wide(q, locs, data, nb, w, bias, radius, ksize, dil, dis_norm, fn):
+    L = nat.lib()
+    B, N, D = locs.shape
+    M, C, K, O, nc = q.shape[1], data.shape[2], nb.shape[2], w.shape[0], w.shape[2]
+    wsb = L.spnb_convsp_forward_wide_workspace_bytes(O, C, D, nc)
+    assert wsb > 0, "shape not supported by the wide path"
+    ws = torch.empty(wsb // 4 + 1, device="cuda")
+    out = torch.empty(B, M, O, device="cuda")
+    nat.check(L.spnb_convsp_forward_wide(nat.ptr(q), nat.ptr(locs), nat.ptr(data), nat.ptr(nb), nat.ptr(w),
+                                         nat.ptr(bias), B, M, N, C, D, K, O, nc, float(radius),
+                                         nat.ptr(ksize), nat.ptr(dil), int(dis_norm), int(fn),
+                                         nat.ptr(out), nat.ptr(ws), wsb, nat.stream()), "convsp_forward_wide")
+    return out

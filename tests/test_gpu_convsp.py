@@ -238,3 +238,42 @@ def test_gradcheck_double_numeric(spn):
             num[mi] = (f(hi) - f(lo)) / (2 * eps)
         a = gu.host(g).astype(np.float64)
         assert np.all(np.abs(a - num) <= 1e-3 + 1e-1 * np.abs(num)), ("gradcheck arg %d" % ai)
+
+
+@pytest.mark.parametrize("D,ks,C,O,fn,dn", [(3, (3, 3, 3), 64, 64, "spiky", 0), (3, (5, 5, 5), 64, 64, "spiky", 0),
+                                           (3, (3, 1, 3), 32, 8, "dspiky", 1), (2, (3, 3), 96, 70, "default", 0),
+                                           (1, (5,), 36, 3, "cohesion", 1)])
+def test_wide_channel_forward(spn, oracle, D, ks, C, O, fn, dn):
+    """BASELINE.json config 3 shape (64 -> 64, kernel_size 5) and relatives through the factored
+    wide-channel kernel (csrc/convsp_wide.cu), against the oracle on a query subset."""
+    B, N, M = 2, 400, 37
+    r = cases.rng(8)
+    R = {1: 0.01, 2: 0.08, 3: 0.2}[D]
+    dil = 0.4 * R
+    locs = r.rand(B, N, D).astype(np.float32)
+    qlocs = r.rand(B, M, D).astype(np.float32)
+    data = r.randn(B, N, C).astype(np.float32)
+    weight = (r.randn(O, C, int(np.prod(ks))) / np.sqrt(C * np.prod(ks))).astype(np.float32)
+    bias = r.rand(O).astype(np.float32)
+    nl, nd, q, nb = build_lists(oracle, locs, data, qlocs, R + dil * max((k - 1) / 2 for k in ks), K=64)
+    assert (nb >= 0).sum() > 4 * B * M
+    ks_np, dil_np = np.array(ks, np.float32), np.full(D, dil, np.float32)
+    want = oracle.convsp_forward(q, nl, nd, nb, weight, bias, R, ks_np, dil_np, dn, fn)
+    got = gu.convsp_forward_wide(gu.dev(q), gu.dev(nl), gu.dev(nd), gu.dev(nb), gu.dev(weight), gu.dev(bias), R,
+                                 gu.dev(ks_np), gu.dev(dil_np), dn, cases.KERNEL_NAMES.index(fn))
+    # signed data and weights: terms cancel, so the absolute tolerance follows the magnitude of the terms
+    terms = oracle.convsp_forward(q, nl, np.abs(nd), nb, np.abs(weight), np.abs(bias), R, ks_np, dil_np, dn, fn)
+    gu.assert_close(gu.host(got), want, RTOL, 1e-6 * max(1.0, float(np.abs(terms).max())), "wide fwd")
+    # the module picks the wide kernel by itself for these shapes (transpose + kernel = 2 launches)
+    from smoothparticlenets_b200 import _native as nat
+    conv = spn.ConvSP(C, O, D, ks, dil, R, dis_norm=bool(dn), kernel_fn=fn).cuda()
+    conv.weight.data.copy_(gu.dev(weight))
+    conv.bias.data.copy_(gu.dev(bias))
+    n0 = nat.lib().spnb_launch_count()
+    with torch.no_grad():
+        out = conv(gu.dev(nl), gu.dev(nd), gu.dev(nb), gu.dev(q))
+    if C * O * int(np.prod(ks)) >= 4096:
+        assert nat.lib().spnb_launch_count() - n0 == 2
+        assert torch.equal(out, got)
+    else:  # small weight tensors stay on the generic kernel
+        gu.assert_close(gu.host(out), want, RTOL, 1e-6 * max(1.0, float(np.abs(terms).max())), "module fwd")

@@ -128,6 +128,27 @@ def main():
         "gC_fwd": (group_fwd(model_f.group_c, mkC), P * fb(3, 3)),
         "gC_fb": (group_fb(model_f.group_c, mkC), P * (fb(3, 3) + bb(3, 3))),
     }
+    if "wide" in only:
+        # config 3: 64 -> 64, kernel_size 5, collision radius 0.2 (n-bar ~ 63), 16384 queries of a 1M scene
+        import numpy as np
+        Nw, Mw = 1 << 20, 1 << 14
+        rr = cases.rng(1)
+        Lw = (Nw / 1910.0) ** (1 / 3.0)
+        wl = torch.from_numpy((rr.rand(1, Nw, 3) * Lw).astype(np.float32)).cuda()
+        wd = torch.randn(1, Nw, 64, device="cuda")
+        wcoll = spn.ParticleCollision(3, 0.2).cuda()
+        wconv = spn.ConvSP(64, 64, 3, 5, 0.05, 0.1, kernel_fn="spiky").cuda()
+        with torch.no_grad():
+            wconv.weight.normal_(0, 0.01)
+            wconv.bias.zero_()
+            wq = wl[:, :Mw].contiguous()
+            wsl, widx, wnb = wcoll(wl, qlocs=wq)
+            wsd = spn.ReorderData()(widx, wl, wd)[1]
+
+        def wide():
+            with torch.no_grad():
+                wconv(wsl, wsd, wnb, wq)
+        table["wide"] = (wide, Mw * 4 * (3 + 64 + 64 + 64))
     print("nbar %.2f  peak %.0f GB/s" % (nbar, peak))
     for name, (fn, byts) in table.items():
         if name not in only:
