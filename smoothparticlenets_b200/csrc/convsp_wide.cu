@@ -11,7 +11,7 @@
 // [queries x (ncells*C)] x [(ncells*C) x O] contraction (1.02 MFLOP per query at c3).
 //
 // One CTA owns kTQ = 8 queries (one warp each).  The kernel cells are processed in slabs whose G
-// tile fits in shared memory (8 queries x 64 cells x 64 channels x 4 B = 128 KB):
+// tile fits in shared memory twice per SM (8 queries x 42 cells x 64 channels x 4 B = 86 KB at c3):
 //   phase 1 (gather): each warp walks its query's neighbour list; for a neighbour the 32 lanes test
 //     32 kernel cells at once (exact fp32 predicate, the reference's float/double W evaluation), the
 //     hits are enumerated with ballot/ffs, and for each hit cell the lanes add W*norm*data[j, c] for
@@ -30,7 +30,7 @@ namespace {
 
 constexpr int kTQ = 8;         // queries per CTA (one warp each)
 constexpr int kWThreads = 256;
-constexpr int kMaxGBytes = 128 * 1024;
+constexpr int kMaxGBytes = 108 * 1024;  // G tile per CTA: two CTAs per SM (227 KB of shared memory)
 
 // Wt[cell][c][o] = weight[o][c][cell]
 __global__ void __launch_bounds__(256)
@@ -55,7 +55,7 @@ k_convsp_wide_fwd(const float* __restrict__ qlocs, const float* __restrict__ loc
                   int O, int ncells, int slab_cells, float radius, const float* __restrict__ ksize,
                   const float* __restrict__ dilation, int dis_norm, SphParams sp, float* __restrict__ out)
 {
-    extern __shared__ __align__(16) float s_G[];  // [kTQ][slab_cells*C]
+    extern __shared__ __align__(16) float s_G[];  // [kTQ][slab_cells*C] then [slab_cells][D] cell offsets
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int m = blockIdx.x * kTQ + warp;
@@ -63,6 +63,7 @@ k_convsp_wide_fwd(const float* __restrict__ qlocs, const float* __restrict__ loc
     const size_t q = (size_t)b * M + (active ? m : 0);
     const int SK = slab_cells * C;  // K-columns per slab
     float* Gq = s_G + (size_t)warp * SK;
+    float* s_off = s_G + (size_t)kTQ * SK;  // (idx_k - ks_k/2) * dilation_k of every cell of the slab
 
     // kernel shape and the cull radius (common_funcs.h:481-485)
     int ks[D], half[D];
@@ -95,7 +96,16 @@ k_convsp_wide_fwd(const float* __restrict__ qlocs, const float* __restrict__ loc
         const int ncs = min(slab_cells, ncells - cell0);
         // ---- phase 1: G tile of this slab
         for (int i = lane; i < SK; i += 32) Gq[i] = 0.0f;
-        __syncwarp();
+        for (int cl = threadIdx.x; cl < ncs; cl += kWThreads) {
+            int rem = cell0 + cl;  // kernel cell index, dimension 0 fastest (common_funcs.h:494,575-580)
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const int ik = rem % ks[k];
+                rem /= ks[k];
+                s_off[cl * D + k] = (ik - half[k]) * dil[k];
+            }
+        }
+        __syncthreads();
         if (active) {
             for (int jj = 0; jj < K; ++jj) {
                 const float nb = row[jj];
@@ -114,18 +124,14 @@ k_convsp_wide_fwd(const float* __restrict__ qlocs, const float* __restrict__ loc
 #pragma unroll
                 for (int i = 0; i < 4; ++i) djr[i] = lane + 32 * i < C ? dj[lane + 32 * i] : 0.0f;
                 for (int r0 = 0; r0 < ncs; r0 += 32) {
-                    const int cl = r0 + lane;       // cell within the slab
-                    const int cell = cell0 + cl;    // global kernel cell, dimension 0 fastest
+                    const int cl = r0 + lane;  // cell within the slab
                     float s = 0.0f;
                     bool hit = false;
                     if (cl < ncs) {
-                        int rem = cell;
                         float d = 0.0f;
 #pragma unroll
                         for (int k = 0; k < D; ++k) {
-                            const int ik = rem % ks[k];
-                            rem /= ks[k];
-                            const float t = x[k] + (ik - half[k]) * dil[k] - y[k];
+                            const float t = x[k] + s_off[cl * D + k] - y[k];
                             d += t * t;
                         }
                         if (d < rad2) {
@@ -162,21 +168,19 @@ k_convsp_wide_fwd(const float* __restrict__ qlocs, const float* __restrict__ loc
                 const int o = t * 64 + o_t;
                 if (o < O) {
                     float a0 = acc[t][0], a1 = acc[t][1];
+                    const float* wp = wslab + o;
                     int k = 0;
-                    for (; k + 4 <= nk; k += 4) {
+                    for (; k + 4 <= nk; k += 4, wp += 4 * O) {
                         const float4 g0 = *reinterpret_cast<const float4*>(G0 + k);
                         const float4 g1 = *reinterpret_cast<const float4*>(G1 + k);
-                        const float w0 = wslab[(size_t)(k + 0) * O + o];
-                        const float w1 = wslab[(size_t)(k + 1) * O + o];
-                        const float w2 = wslab[(size_t)(k + 2) * O + o];
-                        const float w3 = wslab[(size_t)(k + 3) * O + o];
+                        const float w0 = wp[0], w1 = wp[O], w2 = wp[2 * O], w3 = wp[3 * O];
                         a0 = fmaf(g0.x, w0, a0); a1 = fmaf(g1.x, w0, a1);
                         a0 = fmaf(g0.y, w1, a0); a1 = fmaf(g1.y, w1, a1);
                         a0 = fmaf(g0.z, w2, a0); a1 = fmaf(g1.z, w2, a1);
                         a0 = fmaf(g0.w, w3, a0); a1 = fmaf(g1.w, w3, a1);
                     }
-                    for (; k < nk; ++k) {
-                        const float w0 = wslab[(size_t)k * O + o];
+                    for (; k < nk; ++k, wp += O) {
+                        const float w0 = wp[0];
                         a0 = fmaf(G0[k], w0, a0);
                         a1 = fmaf(G1[k], w0, a1);
                     }
@@ -240,7 +244,10 @@ int spnb_convsp_forward_wide(const float* qlocs, const float* locs, const float*
     k_wide_transpose<<<148 * 4, 256, 0, stream>>>(weight, wt, O, C, ncells);
     int slab_cells = kMaxGBytes / (kTQ * C * (int)sizeof(float));
     if (slab_cells > ncells) slab_cells = ncells;
-    const size_t smem = sizeof(float) * (size_t)kTQ * slab_cells * C;
+    // balance the slabs (e.g. 125 cells -> 42, 42, 41 rather than 52, 52, 21)
+    const int nslabs = cdiv(ncells, slab_cells);
+    slab_cells = cdiv(ncells, nslabs);
+    const size_t smem = sizeof(float) * ((size_t)kTQ * slab_cells * C + (size_t)slab_cells * D);
     const dim3 grid(cdiv(M, kTQ), B);
 #define LAUNCH(DD)                                                                                 \
     do {                                                                                           \
