@@ -221,8 +221,11 @@ __device__ __forceinline__ void layer_scales(const GroupArgs& ga, const SphF& sp
 }
 
 // ---- forward ----------------------------------------------------------------------------------------
+#ifndef SPNB_GROUP_FWD_MINB
+#define SPNB_GROUP_FWD_MINB 1
+#endif
 template <typename SG>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, SPNB_GROUP_FWD_MINB)
 k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N,
             int K)
 {
@@ -318,8 +321,11 @@ k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
 // ---- backward ---------------------------------------------------------------------------------------
 // dlocs [B,N,D]: d(sum_l loss_l)/d(locs) through the geometry (query role + neighbour role).
 // ddata_l [B,N,C_l] (may be NULL).  sym: gather; else scatter with atomics into zero-filled buffers.
+#ifndef SPNB_GROUP_BWD_MINB
+#define SPNB_GROUP_BWD_MINB 1
+#endif
 template <typename SG>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, SPNB_GROUP_BWD_MINB)
 k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N,
             int K, float* dlocs, const int* sym_flag)
 {

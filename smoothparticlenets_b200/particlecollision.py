@@ -116,10 +116,14 @@ class ParticleCollision(torch.nn.Module):
             setattr(self, name, buf)
         return buf
 
-    def forward(self, locs, data=None, qlocs=None):
+    def forward(self, locs, data=None, qlocs=None, query_range=None):
         """Returns (locs, [data], idxs, neighbors) exactly as the reference
         (ParticleCollision.py:104-203): locs/data reordered by hash-grid cell, idxs[b,i] = original
-        index of the particle now at i, neighbors BxMxK float lists terminated by -1."""
+        index of the particle now at i, neighbors BxMxK float lists terminated by -1.
+
+        query_range=(start, end) is an extension for splitting ONE scene over several GPUs
+        (scene_parallel.py): the queries are the reordered particles start..end-1 only, so neighbors
+        is Bx(end-start)xK -- the rows start..end-1 of what the call without it returns."""
         batch_size = locs.size()[0]
         N = locs.size()[1]
         ec.check_tensor_dims(locs, "locs", (batch_size, N, self.ndim))
@@ -164,6 +168,13 @@ class ParticleCollision(torch.nn.Module):
         else:
             locs = self.reorder(idxs, locs)
 
+        if query_range is not None:
+            if qlocs is not None:
+                raise ValueError("query_range and qlocs are mutually exclusive")
+            qs, qe = int(query_range[0]), int(query_range[1])
+            if not (0 <= qs < qe <= N):
+                raise ValueError("query_range must satisfy 0 <= start < end <= N")
+            qlocs = locs.detach()[:, qs:qe].contiguous()
         with torch.no_grad(), torch.cuda.device(dev):
             q = locs.detach() if qlocs is None else qlocs.detach()
             nat.require_cuda_f32(q, "qlocs")

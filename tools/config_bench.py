@@ -127,9 +127,46 @@ def c4(B=4, N=262144, S=16):
                                         100 * inside))
 
 
+def c5(N=1 << 24):
+    """Single scene of 2^24 particles (the float32 index limit of the API) on ONE GPU."""
+    D = 3
+    r = cases.rng(3)
+    L = (N / 7640.0) ** (1 / 3.0)
+    locs = torch.from_numpy((r.rand(1, N, D) * L).astype(np.float32)).cuda()
+    vel = torch.rand(1, N, D, device="cuda")
+    coll = spn.ParticleCollision(D, 0.1, max_grid_dim=160, include_self=False).cuda()
+    t_coll = ev(lambda: coll(locs, vel), iters=2, warm=1)
+    sl, sv, idxs, nb = coll(locs, vel)
+    keys = coll.cellIDs[:1].view(torch.int32).view(1, N)
+    ok_sorted = bool((keys[:, 1:] >= keys[:, :-1]).all())
+    ok_perm = bool((idxs.sort(1).values == torch.arange(N, device="cuda", dtype=torch.float32)).all())
+    nbar = float((nb >= 0).sum()) / N
+    ones = torch.ones(1, N, 1, device="cuda")
+    c1 = spn.ConvSP(1, 1, D, 1, 1, 0.1, kernel_fn="spiky", with_params=False).cuda()
+    c3_ = spn.ConvSP(3, 3, D, 1, 1, 0.1, dis_norm=True, kernel_fn="dspiky", with_params=False).cuda()
+    for c in (c1, c3_):
+        c.weight.zero_()
+        c.bias.zero_()
+        for i in range(c.nchannels):
+            c.weight[i, i, 0] = 1
+    l = sl.detach().requires_grad_(True)
+    go1, go3 = torch.rand(1, N, 1, device="cuda"), torch.rand(1, N, 3, device="cuda")
+
+    def fb(conv, data, go):
+        def run():
+            out = conv(l, data, nb)
+            torch.autograd.grad(out, [l], go)
+        return run
+    t1, t3 = ev(fb(c1, ones, go1), iters=3, warm=1), ev(fb(c3_, sv, go3), iters=3, warm=1)
+    print("c5  N=2^24 one scene, grid %s: ParticleCollision %.1f ms (%.0f M particles/s), sorted=%s perm=%s "
+          "n-bar %.1f; ConvSP 1->1 fwd+bwd %.1f ms, 3->3 fwd+bwd %.1f ms; peak memory %.1f GB" % (
+              coll.last_grid_dims.tolist(), t_coll, N / t_coll / 1e3, ok_sorted, ok_perm, nbar, t1, t3,
+              torch.cuda.max_memory_allocated() / 2 ** 30))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c1", "c3", "c4"]
     for w in which:
         t0 = time.time()
-        {"c1": c1, "c3": c3, "c4": c4}[w]()
+        {"c1": c1, "c3": c3, "c4": c4, "c5": c5}[w]()
         print("    (%s took %.1f s wall)" % (w, time.time() - t0))
