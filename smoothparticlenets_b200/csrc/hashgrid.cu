@@ -332,25 +332,26 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
 }
 
 // ---- reorder -------------------------------------------------------------------------------------
-// One thread per output float.  reverse == 0: out[b,i,:] = in[b,idxs[b,i],:]; else scatter.
+// One thread per output float of one tensor (z = 0: locs, z = 1: data), blockIdx.y = scene, 32-bit
+// index math with a compile-time row width where it is small.  reverse == 0: out[i,:] = in[idxs[i],:]
+// (coalesced writes, row gathers); else out[idxs[i],:] = in[i,:].
+template <int WT>
 __global__ void __launch_bounds__(256)
 k_reorder(const float* __restrict__ locs, const float* __restrict__ data,
-          const float* __restrict__ idxs, float* __restrict__ nlocs, float* __restrict__ ndata,
-          long long BN, int N, int D, int C, int reverse)
+          const float* __restrict__ idxs, float* __restrict__ nlocs, float* __restrict__ ndata, int N,
+          int D, int C, int reverse)
 {
-    const long long nl = BN * D, total = nl + BN * (long long)C;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const bool is_loc = e < nl;
-        const long long ee = is_loc ? e : e - nl;
-        const int W = is_loc ? D : C;
-        const long long row = ee / W;
-        const int col = (int)(ee - row * W);
-        const long long scene0 = row - row % N;
-        const long long other = scene0 + (long long)idxs[row];
-        const long long src = reverse ? row : other, dst = reverse ? other : row;
-        if (is_loc) nlocs[dst * D + col] = locs[src * D + col];
-        else ndata[dst * C + col] = data[src * C + col];
+    const bool is_loc = blockIdx.z == 0;
+    const int W = WT > 0 ? WT : (is_loc ? D : C);
+    const float* __restrict__ in = (is_loc ? locs : data) + (size_t)blockIdx.y * N * W;
+    float* __restrict__ out = (is_loc ? nlocs : ndata) + (size_t)blockIdx.y * N * W;
+    const float* __restrict__ ix = idxs + (size_t)blockIdx.y * N;
+    const unsigned total = (unsigned)N * (unsigned)W;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const unsigned row = e / (unsigned)W, col = e - row * (unsigned)W;
+        const unsigned other = (unsigned)(int)ix[row];
+        if (reverse) out[other * W + col] = in[e];
+        else out[e] = in[other * W + col];
     }
 }
 
@@ -660,10 +661,42 @@ int spnb_reorder_data(const float* locs, const float* data, const float* idxs, f
         return 0;
     }
     if (!data) C = 0;
-    const long long BN = (long long)B * N;
-    int blocks = cdiv(BN * (D + C), 256);
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    k_reorder<<<blocks, 256, 0, stream>>>(locs, data, idxs, nlocs, ndata, BN, N, D, C, reverse);
+    if ((long long)N * (D > C ? D : C) >= (1ll << 32)) {
+        set_error("spnb_reorder_data: N * row width exceeds 2^32");
+        return 0;
+    }
+    // one tensor per launch (used when the row widths of locs and data differ): the kernel reads its
+    // tensor from the `locs` slot (blockIdx.z == 0)
+    auto launch = [&](int W, const float* in, float* out) {
+        int blocks = cdiv((long long)N * W, 256 * 4);
+        if (blocks < 1) blocks = 1;
+        const dim3 grid(blocks, B, 1);
+        switch (W) {
+        case 1: k_reorder<1><<<grid, 256, 0, stream>>>(in, nullptr, idxs, out, nullptr, N, W, 0, reverse); break;
+        case 2: k_reorder<2><<<grid, 256, 0, stream>>>(in, nullptr, idxs, out, nullptr, N, W, 0, reverse); break;
+        case 3: k_reorder<3><<<grid, 256, 0, stream>>>(in, nullptr, idxs, out, nullptr, N, W, 0, reverse); break;
+        case 4: k_reorder<4><<<grid, 256, 0, stream>>>(in, nullptr, idxs, out, nullptr, N, W, 0, reverse); break;
+        default: k_reorder<0><<<grid, 256, 0, stream>>>(in, nullptr, idxs, out, nullptr, N, W, 0, reverse); break;
+        }
+    };
+    if (C == D && D <= 4) {
+        // both tensors in one launch (gridDim.z = 2)
+        int blocks = cdiv((long long)N * D, 256 * 4);
+        if (blocks < 1) blocks = 1;
+        const dim3 grid(blocks, B, 2);
+        switch (D) {
+        case 1: k_reorder<1><<<grid, 256, 0, stream>>>(locs, data, idxs, nlocs, ndata, N, D, C, reverse); break;
+        case 2: k_reorder<2><<<grid, 256, 0, stream>>>(locs, data, idxs, nlocs, ndata, N, D, C, reverse); break;
+        case 3: k_reorder<3><<<grid, 256, 0, stream>>>(locs, data, idxs, nlocs, ndata, N, D, C, reverse); break;
+        default: k_reorder<4><<<grid, 256, 0, stream>>>(locs, data, idxs, nlocs, ndata, N, D, C, reverse); break;
+        }
+    } else {
+        launch(D, locs, nlocs);
+        if (C > 0) {
+            launch(C, data, ndata);
+            count_launches(1);
+        }
+    }
     count_launches(1);
     return check_launch("spnb_reorder_data") ? 1 : 0;
 }

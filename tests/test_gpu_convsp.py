@@ -277,3 +277,44 @@ def test_wide_channel_forward(spn, oracle, D, ks, C, O, fn, dn):
         assert torch.equal(out, got)
     else:  # small weight tensors stay on the generic kernel
         gu.assert_close(gu.host(out), want, RTOL, 1e-6 * max(1.0, float(np.abs(terms).max())), "module fwd")
+
+
+def test_full_size_properties(spn):
+    """BASELINE.json config 2 size (8 x 65536 particles): size-independent properties of ConvSP --
+    the `constant` kernel with unit data counts neighbours, outputs are linear in the data, the fused
+    group path equals the per-layer path, and the two backward modes (symmetric gather / atomics) agree."""
+    B, N, R = 8, 65536, 0.1
+    locs, vel, _ = cases.fluid_cloud(0, B, N)
+    coll = spn.ParticleCollision(3, R, include_self=False).cuda()
+    sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
+    ones = torch.ones(B, N, 1, device="cuda")
+
+    def layer(kernel, C, normed):
+        c = spn.ConvSP(C, C, 3, 1, 1, R, dis_norm=normed, with_params=False, kernel_fn=kernel).cuda()
+        c.weight.zero_()
+        c.bias.zero_()
+        for i in range(C):
+            c.weight[i, i, 0] = 1
+        return c
+    count = layer("constant", 1, False)(sl, ones, nb)
+    assert torch.equal(count[..., 0], (nb >= 0).sum(2).float()), "constant kernel counts the list entries"
+    spiky3 = layer("spiky", 3, False)
+    a, b_ = spiky3(sl, sv, nb), spiky3(sl, 2.0 * sv + 1.0, nb)
+    dens = layer("spiky", 1, False)(sl, ones, nb)
+    lin = 2.0 * a + dens  # W-weighted sum of (2 v + 1) = 2 * sum(W v) + sum(W)
+    assert float((b_ - lin).abs().max()) <= 2e-5 * float(lin.abs().max()), "linearity in the data"
+    group = spn.ConvSPGroup([spiky3, layer("spiky", 1, False)])
+    g3, g1 = group(sl, [sv, ones], nb)
+    assert float((g3 - a).abs().max()) <= 1e-5 * float(a.abs().max())
+    assert float((g1 - dens).abs().max()) <= 1e-5 * float(dens.abs().max())
+    # backward: symmetric gather (tagged lists) vs atomics (untagged copy of the same lists)
+    go = torch.rand(B, N, 3, device="cuda")
+    dsp = layer("dspiky", 3, True)
+    grads = []
+    for lists in (nb, nb.clone()):
+        l = sl.detach().clone().requires_grad_(True)
+        d = sv.detach().clone().requires_grad_(True)
+        dsp(l, d, lists).backward(go)
+        grads.append((l.grad, d.grad))
+    for x, y in zip(*grads):
+        assert float((x - y).abs().max()) <= 2e-5 * float(y.abs().max()), "gather and atomic backward agree"
