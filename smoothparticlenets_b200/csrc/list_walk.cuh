@@ -17,13 +17,49 @@
 
 namespace spnb {
 
+// Row staging: 0 = cp.async (LDGSTS, 16 bytes per lane), 1 = one cp.async.bulk (TMA 1-D bulk copy,
+// UBLKCP) per 128-byte row chunk completing on a per-warp mbarrier.  Both are kept; the A/B on one B200
+// (tools/ab_test.sh, profiles/README.md) has LDGSTS 5-10 % faster for these 128-byte transfers (the
+// mbarrier arm/try_wait round trip per chunk costs more than it saves), so it is the default.
+#ifndef SPNB_WALK_TMA
+#define SPNB_WALK_TMA 0
+#endif
+
 template <int G>
 struct WalkSmem {
     static constexpr int R = 32 / G;       // queries per warp
     static constexpr int STRIDE = 32 + G;  // floats per staged row: group g starts at bank g*G
-    float nb[R * STRIDE];
+    alignas(16) float nb[R * STRIDE];
     int cnt[R];
+    alignas(8) unsigned long long bar;     // mbarrier of this warp's row copies (TMA staging)
 };
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier.
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
@@ -53,11 +89,27 @@ __device__ __forceinline__ void walk_rows(const float* __restrict__ warp_rows, i
     const int g = lane / G, sub = lane % G;
     const bool aligned = ((K & 3) == 0) && ((reinterpret_cast<size_t>(warp_rows) & 15) == 0);
     bool mine = g < nrows;  // my group's row is still being walked
+#if SPNB_WALK_TMA
+    unsigned parity = 0;
+    if (lane == 0) mbar_init(&sm.bar, 1);
+    __syncwarp();
+#endif
     for (int base = 0; base < K; base += 32) {
         if (!__any_sync(0xffffffffu, mine)) break;
         __syncwarp();  // the previous chunk has been consumed by every lane
         int cnt = 0;
         if (aligned && base + 32 <= K) {
+#if SPNB_WALK_TMA
+            // one 128-byte TMA bulk copy per live row, issued by the first lane of the row's group;
+            // lane 0 arms the warp's mbarrier with the byte count, everybody waits on its phase
+            const unsigned live = __ballot_sync(0xffffffffu, mine && sub == 0);
+            if (lane == 0) mbar_expect_tx(&sm.bar, 128u * __popc(live));
+            __syncwarp();
+            if (mine && sub == 0)
+                bulk_copy_g2s(&sm.nb[g * STRIDE], warp_rows + (size_t)g * K + base, 128u, &sm.bar);
+            mbar_wait(&sm.bar, parity);
+            parity ^= 1u;
+#else
             if (mine) {
                 const float* src = warp_rows + (size_t)g * K + base;
 #pragma unroll
@@ -66,6 +118,7 @@ __device__ __forceinline__ void walk_rows(const float* __restrict__ warp_rows, i
             }
             cp_async_wait_all();
             __syncwarp();
+#endif
             // first negative entry among mine (positions sub, sub+G, ...), then over the group
             int first = 32;
             if (mine) {
