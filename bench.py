@@ -162,6 +162,7 @@ def time_kernels(torch, spn, model, locs, vel, iters=10):
         sl, sv, idxs, nb = model.coll(locs, vel)
     nbar = float((nb >= 0).sum().item()) / (B * N)
     flag = nb._spnb_sym_flag
+    tiles = getattr(nb, "_spnb_tiles", None)
     ones = torch.ones(B, N, 1, device="cuda")
     go1, go3 = torch.rand(B, N, 1, device="cuda"), torch.rand(B, N, 3, device="cuda")
     def ev_time(fn):
@@ -235,10 +236,11 @@ def time_kernels(torch, spn, model, locs, vel, iters=10):
         wsf = torch.empty(wf // 4 + 1, device="cuda")
         wsb = torch.empty(wb // 4 + 1, device="cuda")
         f_fn = lambda afw=afw, wsf=wsf, wf=wf, n=len(cfg): L.spnb_convsp_group_forward(
-            nat.ptr(sl), nat.ptr(nb), B, N, D, nb.shape[2], float(RADIUS), n, afw, nat.ptr(wsf), wf, nat.stream())
+            nat.ptr(sl), nat.ptr(nb), B, N, D, nb.shape[2], float(RADIUS), n, afw, nat.ptr(wsf), wf, nat.ptr(tiles),
+            nat.stream())
         b_fn = lambda abw=abw, wsb=wsb, wb=wb, n=len(cfg), dl=dl: L.spnb_convsp_group_backward(
             nat.ptr(sl), nat.ptr(nb), B, N, D, nb.shape[2], float(RADIUS), n, abw, nat.ptr(dl), nat.ptr(flag),
-            nat.ptr(wsb), wb, nat.stream())
+            nat.ptr(wsb), wb, nat.ptr(tiles), nat.stream())
         # SURVEY 8(d) bytes of the layers this op replaces, and the op's own compulsory bytes
         eq_f = sum(fb(c[2], c[3]) for c in cfg)
         eq_b = sum(bb(c[2], c[3]) for c in cfg)

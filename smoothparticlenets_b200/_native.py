@@ -23,6 +23,8 @@ _SIGNATURES = {
     "spnb_grid_bounds": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "spnb_hashgrid_order": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _i, _vp]),
     "spnb_compute_collisions": (_i, [_vp] * 8 + [_i] * 6 + [_f, _f, _i, _vp, _vp]),
+    "spnb_tile_lists_bytes": (_sz, [_i, _i, _i, _i]),
+    "spnb_compute_collisions_tiled": (_i, [_vp] * 8 + [_i] * 6 + [_f, _f, _i, _vp, _vp, _sz, _vp]),
     "spnb_reorder_data": (_i, [_vp] * 5 + [_i] * 5 + [_vp]),
     "spnb_convsp_forward": (_i, [_vp] * 6 + [_i] * 8 + [_f, _vp, _vp, _i, _i, _vp, _vp]),
     "spnb_convsp_forward_wide_workspace_bytes": (_sz, [_i, _i, _i, _i]),
@@ -30,8 +32,8 @@ _SIGNATURES = {
     "spnb_convsp_backward_workspace_bytes": (_sz, [_i, _i, _i]),
     "spnb_convsp_backward": (_i, [_vp] * 5 + [_i] * 8 + [_f, _vp, _vp, _i, _i] + [_vp] * 8),
     "spnb_convsp_group_workspace_bytes": (_sz, [_vp, _i, _i, _i, _f, _i, _vp, _i]),
-    "spnb_convsp_group_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _sz, _vp]),
-    "spnb_convsp_group_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "spnb_convsp_group_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _sz, _vp, _vp]),
+    "spnb_convsp_group_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "spnb_convsdf_forward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp, _i, _vp,
                                   _vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "spnb_convsdf_backward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp, _i, _vp,

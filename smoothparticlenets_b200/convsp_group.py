@@ -48,10 +48,11 @@ class ConvSPGroup(torch.nn.Module):
             locs_c = locs.contiguous()
             datas_c = [d.contiguous() for d in datas]
             sym_flag = getattr(neighbors, "_spnb_sym_flag", None)
+            tiles = getattr(neighbors, "_spnb_tiles", None)
             cfg = tuple((l.kernel_fn, l.dis_norm, l.nchannels, l.nkernels) for l in layers)
             flat = list(datas_c) + [l.weight for l in layers] + [l.bias for l in layers]
             if _supported(locs_c, datas_c, layers, cfg):
-                return _ConvSPGroupFunction.apply(locs_c, neighbors.contiguous(), sym_flag,
+                return _ConvSPGroupFunction.apply(locs_c, neighbors.contiguous(), (sym_flag, tiles),
                                                   float(layers[0].radius), cfg, *flat)
         return tuple(l(locs, d, neighbors) for l, d in zip(layers, datas))
 
@@ -80,7 +81,11 @@ def _supported(locs, datas, layers, cfg):
 class _ConvSPGroupFunction(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, locs, neighbors, sym_flag, radius, cfg, *flat):
+    def forward(ctx, locs, neighbors, flags, radius, cfg, *flat):
+        sym_flag, tiles = flags
+        if tiles is not None and tiles.numel() != nat.lib().spnb_tile_lists_bytes(
+                locs.shape[0], locs.shape[1], locs.shape[2], neighbors.shape[2]):
+            tiles = None  # not the sidecar of a tensor of this shape
         n = len(cfg)
         datas, weights, biases = flat[:n], flat[n:2 * n], flat[2 * n:3 * n]
         for t in (locs, neighbors) + tuple(flat):
@@ -94,10 +99,10 @@ class _ConvSPGroupFunction(torch.autograd.Function):
         ws = torch.empty((wsb + 3) // 4, device=locs.device, dtype=torch.float32)
         with torch.cuda.device(locs.device):
             nat.check(L.spnb_convsp_group_forward(nat.ptr(locs), nat.ptr(neighbors), B, N, D, K, radius, n,
-                                                  arr, nat.ptr(ws), wsb, nat.stream()),
+                                                  arr, nat.ptr(ws), wsb, nat.ptr(tiles), nat.stream()),
                       "spnb_convsp_group_forward")
         ctx.save_for_backward(locs, neighbors, *datas, *weights)
-        ctx.cfg, ctx.radius, ctx.sym_flag = cfg, radius, sym_flag
+        ctx.cfg, ctx.radius, ctx.sym_flag, ctx.tiles = cfg, radius, sym_flag, tiles
         return tuple(outs)
 
     @staticmethod
@@ -123,6 +128,7 @@ class _ConvSPGroupFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             nat.check(L.spnb_convsp_group_backward(nat.ptr(locs), nat.ptr(neighbors), B, N, D, K, radius, n,
                                                    arr, nat.ptr(dlocs), nat.ptr(ctx.sym_flag), nat.ptr(ws),
-                                                   wsb, nat.stream()), "spnb_convsp_group_backward")
+                                                   wsb, nat.ptr(ctx.tiles), nat.stream()),
+                      "spnb_convsp_group_backward")
         dbias = [gos[i].sum(1).sum(0) if ctx.needs_input_grad[5 + 2 * n + i] else None for i in range(n)]
         return (dlocs if need_locs else None, None, None, None, None) + tuple(ddatas) + (None,) * n + tuple(dbias)

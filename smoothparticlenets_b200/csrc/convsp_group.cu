@@ -28,6 +28,7 @@
 
 #include "convsp_small.cuh"
 #include "list_walk.cuh"
+#include "tile_lists.cuh"
 
 namespace spnb {
 
@@ -48,7 +49,15 @@ constexpr int kThreads = 128;
 #ifndef SPNB_GROUP_BWD_U
 #define SPNB_GROUP_BWD_U 1
 #endif
+// tile-list kernels (tile_lists.cuh): lanes per query
+#ifndef SPNB_TILE_FWD_G
+#define SPNB_TILE_FWD_G 1
+#endif
+#ifndef SPNB_TILE_BWD_G
+#define SPNB_TILE_BWD_G 2
+#endif
 constexpr int kMaxLayers = 6;
+constexpr int kFallbackGrid = 148 * 4;  // blocks of the strided list-walk fallback of a tiled call
 constexpr unsigned kSrcLocs = 15;  // "data is the position tensor"
 
 // ---- compile-time group signature -------------------------------------------------------------------
@@ -169,8 +178,11 @@ __device__ __forceinline__ float sph_fast(int e, float d, float d2, float c, con
 // rec[n] = [ locs(D) | distinct data ... | (BWD) U_l(C_l) for every layer ], padded to float4s.
 template <typename SG, bool BWD>
 __global__ void __launch_bounds__(256)
-k_group_pack(const float* __restrict__ locs, GroupArgs ga, long long BN, float* __restrict__ rec)
+k_group_pack(const float* __restrict__ locs, GroupArgs ga, long long BN, float* __restrict__ rec,
+             const int* __restrict__ tile_flag, float* __restrict__ dlocs, const int* __restrict__ sym_flag)
 {
+    // planar (one float4 array per record quarter) for the tile kernels, record-major for the list walk
+    const bool planar = tile_flag != nullptr && *tile_flag == 0;
     constexpr int V = BWD ? SG::bwd_vec() : SG::fwd_vec();
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= BN) return;
@@ -185,6 +197,17 @@ k_group_pack(const float* __restrict__ locs, GroupArgs ga, long long BN, float* 
         for (int c = 0; c < SG::src_channels(s); ++c)
             r[SG::src_off(s) + c] = ga.src[s][n * SG::src_channels(s) + c];
     if (BWD) {
+        if (!(sym_flag != nullptr && *sym_flag == 0)) {
+            // the scatter mode of k_group_bwd accumulates with atomics: its targets start from zero
+#pragma unroll
+            for (int k = 0; k < SG::D; ++k) dlocs[n * SG::D + k] = 0.0f;
+#pragma unroll
+            for (int l = 0; l < SG::NL; ++l)
+                if (ga.l[l].ddata) {
+#pragma unroll
+                    for (int c = 0; c < SG::C(l); ++c) ga.l[l].ddata[n * SG::C(l) + c] = 0.0f;
+                }
+        }
 #pragma unroll
         for (int l = 0; l < SG::NL; ++l) {
             const LayerArgs& L = ga.l[l];
@@ -196,9 +219,10 @@ k_group_pack(const float* __restrict__ locs, GroupArgs ga, long long BN, float* 
             }
         }
     }
-    float4* dst = reinterpret_cast<float4*>(rec) + n * V;
+    float4* dst = reinterpret_cast<float4*>(rec) + (planar ? n : n * V);
+    const long long vs = planar ? BN : 1;
 #pragma unroll
-    for (int v = 0; v < V; ++v) dst[v] = make_float4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+    for (int v = 0; v < V; ++v) dst[v * vs] = make_float4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
 }
 
 // s_l = W_l(d) * norm_l (and t_l = dW_l/dd / d * norm_l) for every layer, evaluated once per distinct
@@ -225,19 +249,17 @@ __device__ __forceinline__ void layer_scales(const GroupArgs& ga, const SphF& sp
 #define SPNB_GROUP_FWD_MINB 1
 #endif
 template <typename SG>
-__global__ void __launch_bounds__(kThreads, SPNB_GROUP_FWD_MINB)
-k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N,
-            int K)
+__device__ __forceinline__ void group_fwd_block(const float* __restrict__ rec, const float* __restrict__ neighbors,
+                                                const GroupArgs& ga, int N, int K, int bx, int b, int nbx, int nby)
 {
     constexpr int D = SG::D, V = SG::fwd_vec(), CT = SG::ctot();
     constexpr int G = SPNB_GROUP_FWD_G, kU = SPNB_GROUP_FWD_U, QPB = kThreads / G, R = 32 / G;
     __shared__ WalkSmem<G> s_walk[kThreads / 32];
     const int warp = threadIdx.x >> 5, sub = threadIdx.x % G;
-    const int b = blockIdx.y;
-    const int m = blockIdx.x * QPB + threadIdx.x / G;
+    const int m = bx * QPB + threadIdx.x / G;
     const bool active = m < N;
     const size_t q = (size_t)b * N + (active ? m : 0);
-    const int m0 = blockIdx.x * QPB + warp * R;  // first query of this warp
+    const int m0 = bx * QPB + warp * R;  // first query of this warp
     const int nrows = min(R, max(0, N - m0));
     const SphF sp = {ga.H, ga.invH, ga.H2};
     const float4* srec = reinterpret_cast<const float4*>(rec) + (size_t)b * N * V;
@@ -252,7 +274,7 @@ k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
 #pragma unroll
     for (int i = 0; i < CT; ++i) G_[i] = 0.0f;
     const float* warp_rows = neighbors + ((size_t)b * N + min(m0, N - 1)) * K;
-    prefetch_rows_ahead(neighbors, N, K, QPB, 2);
+    prefetch_rows_ahead(neighbors, N, K, QPB, 2, bx, b, nbx, nby);
 
     walk_rows<G, kU>(warp_rows, K, nrows, s_walk[warp], [&](const int* j, const bool* valid) {
 #if defined(SPNB_DEBUG_WALK_ONLY)
@@ -318,6 +340,27 @@ k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
     }
 }
 
+// The list walk as a kernel of its own (no tile lists), and as the device-side FALLBACK of a call that
+// has tile lists: a small grid that returns at once when the tile flag is clear (the tile kernel has
+// done the work) and otherwise strides over the blocks.
+template <typename SG>
+__global__ void __launch_bounds__(kThreads, SPNB_GROUP_FWD_MINB)
+k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N, int K)
+{
+    group_fwd_block<SG>(rec, neighbors, ga, N, K, blockIdx.x, blockIdx.y, gridDim.x, gridDim.y);
+}
+template <typename SG>
+__global__ void __launch_bounds__(kThreads, SPNB_GROUP_FWD_MINB)
+k_group_fwd_fallback(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N, int K,
+                     int nbx, int B, const int* __restrict__ tile_flag)
+{
+    if (*tile_flag == 0) return;
+    for (int t = blockIdx.x; t < nbx * B; t += gridDim.x) {
+        group_fwd_block<SG>(rec, neighbors, ga, N, K, t % nbx, t / nbx, nbx, B);
+        __syncthreads();
+    }
+}
+
 // ---- backward ---------------------------------------------------------------------------------------
 // dlocs [B,N,D]: d(sum_l loss_l)/d(locs) through the geometry (query role + neighbour role).
 // ddata_l [B,N,C_l] (may be NULL).  sym: gather; else scatter with atomics into zero-filled buffers.
@@ -325,20 +368,19 @@ k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
 #define SPNB_GROUP_BWD_MINB 1
 #endif
 template <typename SG>
-__global__ void __launch_bounds__(kThreads, SPNB_GROUP_BWD_MINB)
-k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N,
-            int K, float* dlocs, const int* sym_flag)
+__device__ __forceinline__ void group_bwd_block(const float* __restrict__ rec, const float* __restrict__ neighbors,
+                                                const GroupArgs& ga, int N, int K, float* dlocs, const int* sym_flag,
+                                                int bx, int b, int nbx, int nby)
 {
     constexpr int D = SG::D, V = SG::bwd_vec(), CT = SG::ctot();
     constexpr int G = SPNB_GROUP_BWD_G, UB = SPNB_GROUP_BWD_U, QPB = kThreads / G, R = 32 / G;
     __shared__ WalkSmem<G> s_walk[kThreads / 32];
     const bool sym = sym_flag != nullptr && *sym_flag == 0;
     const int warp = threadIdx.x >> 5, sub = threadIdx.x % G;
-    const int b = blockIdx.y;
-    const int m = blockIdx.x * QPB + threadIdx.x / G;
+    const int m = bx * QPB + threadIdx.x / G;
     const bool active = m < N;
     const size_t q = (size_t)b * N + (active ? m : 0);
-    const int m0 = blockIdx.x * QPB + warp * R;
+    const int m0 = bx * QPB + warp * R;
     const int nrows = min(R, max(0, N - m0));
     const SphF sp = {ga.H, ga.invH, ga.H2};
     const float4* srec = reinterpret_cast<const float4*>(rec) + (size_t)b * N * V;
@@ -354,7 +396,7 @@ k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
 #pragma unroll
     for (int i = 0; i < CT; ++i) a_dd[i] = 0.0f;
     const float* warp_rows = neighbors + ((size_t)b * N + min(m0, N - 1)) * K;
-    prefetch_rows_ahead(neighbors, N, K, QPB, 2);
+    prefetch_rows_ahead(neighbors, N, K, QPB, 2, bx, b, nbx, nby);
 
     walk_rows<G, UB>(warp_rows, K, nrows, s_walk[warp], [&](const int* j, const bool* valid) {
         float r[UB][V * 4];
@@ -444,6 +486,329 @@ k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, 
     }
 }
 
+
+template <typename SG>
+__global__ void __launch_bounds__(kThreads, SPNB_GROUP_BWD_MINB)
+k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N, int K,
+            float* dlocs, const int* sym_flag)
+{
+    group_bwd_block<SG>(rec, neighbors, ga, N, K, dlocs, sym_flag, blockIdx.x, blockIdx.y, gridDim.x, gridDim.y);
+}
+template <typename SG>
+__global__ void __launch_bounds__(kThreads, SPNB_GROUP_BWD_MINB)
+k_group_bwd_fallback(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N, int K,
+                     float* dlocs, const int* sym_flag, int nbx, int B, const int* __restrict__ tile_flag)
+{
+    if (*tile_flag == 0) return;
+    for (int t = blockIdx.x; t < nbx * B; t += gridDim.x) {
+        group_bwd_block<SG>(rec, neighbors, ga, N, K, dlocs, sym_flag, t % nbx, t / nbx, nbx, B);
+        __syncthreads();
+    }
+}
+
+// ---- tile-list kernels --------------------------------------------------------------------------------
+// Same math as k_group_fwd / k_group_bwd (symmetric mode), but driven by the compact tile lists of
+// tile_lists.cuh: one block per tile block of 64 queries; the planar records of the block's candidate
+// ranges are staged in shared memory by TMA bulk copies (one cp.async.bulk per range and record quarter,
+// completion on an mbarrier), the 16-bit lists are read in coalesced 32-byte units, and every neighbour
+// gather is an LDS.128 instead of an L1/L2 round trip.
+struct TileArgs {
+    const int* flag;
+    const TileDesc* descs;
+    const int* counts;
+    const unsigned char* lists;
+    int ntb;
+};
+
+template <int V>
+__device__ __forceinline__ void tile_stage(const float4* __restrict__ planes, size_t plane_stride, size_t scene_off,
+                                           const TileDesc& d, float4* s_rec, unsigned long long* bar)
+{
+    // warp 0: lane 0 arms the barrier with the byte count, then the lanes issue the copies
+    const int lane = threadIdx.x;
+    const bool fits = d.total + 1 <= kTileCap;  // else: nothing is staged, the block gathers from global memory
+    if (lane == 0) mbar_expect_tx(bar, fits ? (unsigned)d.total * 16u * V : 0u);
+    __syncwarp();
+    const int ncopies = fits ? d.nr * V : 0;
+    for (int i = lane; i < ncopies; i += 32) {
+        const int r = i / V, v = i % V;
+        const int len = d.prefix[r + 1] - d.prefix[r];
+        if (len > 0)
+            bulk_copy_g2s(s_rec + (size_t)v * kTileCap + 1 + d.prefix[r],
+                          planes + (size_t)v * plane_stride + scene_off + d.start[r], (unsigned)len * 16u, bar);
+    }
+}
+
+// sorted particle index of staged slot `slot` (>= 1) -- only the rare blocks whose tile does not fit
+// kTileCap use this (they gather from global memory instead of the staged copy)
+__device__ __forceinline__ int tile_slot_to_index(const TileDesc& d, unsigned slot)
+{
+    const int s = (int)slot - 1;
+    int idx = 0;
+#pragma unroll
+    for (int r = 0; r < kTileMaxRanges; ++r)
+        if (r < d.nr && s >= d.prefix[r]) idx = d.start[r] + s - d.prefix[r];
+    return idx;
+}
+
+template <int G>
+struct TileUnit {
+    static constexpr int WORDS = 8 / G;  // 32-bit words (2 entries each) per lane and unit
+    unsigned w[WORDS];
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int i = 0; i < WORDS; ++i) w[i] = 0u;
+    }
+    __device__ __forceinline__ void load(const unsigned char* p)
+    {
+        if (WORDS == 8) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+            w[4 % WORDS] = b.x; w[5 % WORDS] = b.y; w[6 % WORDS] = b.z; w[7 % WORDS] = b.w;
+        } else if (WORDS == 4) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+            w[0] = a.x; w[1] = a.y; w[2 % WORDS] = a.z; w[3 % WORDS] = a.w;
+        } else {
+            const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+            w[0] = a.x; w[1 % WORDS] = a.y;
+        }
+    }
+};
+
+// Calls body(slot) for every list entry of this lane's share of its query's list (sentinel slots
+// included: they fail every radius test).  Units are prefetched one ahead.
+template <int G, typename Body>
+__device__ __forceinline__ void tile_walk(const unsigned char* __restrict__ my_units, int nunits, Body body)
+{
+    const int wmax = __reduce_max_sync(0xffffffffu, nunits);
+    TileUnit<G> cur, nxt;
+    cur.clear();
+    if (0 < nunits) cur.load(my_units);
+    for (int u = 0; u < wmax; ++u) {
+        nxt.clear();
+        if (u + 1 < nunits) nxt.load(my_units + (size_t)(u + 1) * 256);
+#pragma unroll
+        for (int i = 0; i < TileUnit<G>::WORDS; ++i) {
+            body(cur.w[i] & 0xffffu);
+            body(cur.w[i] >> 16);
+        }
+        cur = nxt;
+    }
+}
+
+template <typename SG, int G>
+__global__ void __launch_bounds__(kTileQ * G)
+k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int K, long long BN)
+{
+    constexpr int D = SG::D, V = SG::fwd_vec(), CT = SG::ctot();
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float4* s_rec = reinterpret_cast<float4*>(s_raw);
+    __shared__ TileDesc s_desc;
+    __shared__ __align__(8) unsigned long long s_bar;
+    if (*ta.flag != 0) return;
+    const int tid = threadIdx.x, tb = blockIdx.x, b = blockIdx.y;
+    if (tid < 32) reinterpret_cast<int*>(&s_desc)[tid] = reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb)[tid];
+    if (tid == 0) mbar_init(&s_bar, 1);
+    if (tid < V) s_rec[tid * kTileCap] = tid == 0 ? make_float4(1e18f, 1e18f, 1e18f, 0.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    __syncthreads();
+    const float4* planes = reinterpret_cast<const float4*>(rec);
+    if (tid < 32) tile_stage<V>(planes, (size_t)BN, (size_t)b * N, s_desc, s_rec, &s_bar);
+
+    const int ql = tid / G, sub = tid % G;
+    const int m = tb * kTileQ + ql;
+    const bool active = m < N;
+    const size_t q = (size_t)b * N + (active ? m : 0);
+    const SphF sp = {ga.H, ga.invH, ga.H2};
+    float x[D];
+    {
+        const float4 r0 = planes[q];
+        const float t[4] = {r0.x, r0.y, r0.z, r0.w};
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[k] = t[k];
+    }
+    const int cnt = active ? ta.counts[q] : 0;
+    const int nunits = (cnt + kTileUnit - 1) / kTileUnit;
+    const unsigned char* my_units = ta.lists + tile_entry_off(ta.ntb, K, b, tb, ql, 0) + sub * (32 / G);
+    float G_[CT];
+#pragma unroll
+    for (int i = 0; i < CT; ++i) G_[i] = 0.0f;
+    mbar_wait(&s_bar, 0);
+
+    auto pair = [&](const float* r) {
+        float d2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const float nr = x[k] - r[k];
+            d2 += nr * nr;
+        }
+        if (d2 < ga.rad2) {
+            const bool pos = d2 > 0.0f;
+            const float inv = fast_rsqrt(d2);
+            const float d = pos ? d2 * inv : 0.0f;
+            float s[SG::NL];
+            layer_scales<SG, false>(ga, sp, d, d2, inv, pos, s, nullptr);
+#pragma unroll
+            for (int l = 0; l < SG::NL; ++l)
+#pragma unroll
+                for (int c = 0; c < SG::C(l); ++c)
+                    G_[SG::chan_off(l) + c] = fmaf(s[l], r[SG::data_off(l) + c], G_[SG::chan_off(l) + c]);
+        }
+    };
+    if (s_desc.total + 1 <= kTileCap) {
+        tile_walk<G>(my_units, nunits, [&](unsigned slot) {
+            float r[V * 4];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float4 t = s_rec[v * kTileCap + slot];
+                r[4 * v] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
+            }
+            pair(r);
+        });
+    } else {
+        tile_walk<G>(my_units, nunits, [&](unsigned slot) {
+            if (slot == 0) return;
+            const size_t j = (size_t)b * N + tile_slot_to_index(s_desc, slot);
+            float r[V * 4];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float4 t = planes[(size_t)v * BN + j];
+                r[4 * v] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
+            }
+            pair(r);
+        });
+    }
+    if (G > 1) {
+#pragma unroll
+        for (int i = 0; i < CT; ++i) G_[i] = group_sum<G>(G_[i]);
+    }
+    if (active) {
+#pragma unroll
+        for (int l = 0; l < SG::NL; ++l) {
+            const LayerArgs& L = ga.l[l];
+            for (int o = sub; o < L.O; o += G) {
+                float v = L.bias ? L.bias[o] : 0.0f;
+#pragma unroll
+                for (int c = 0; c < SG::C(l); ++c) v = fmaf(L.weight[o * SG::C(l) + c], G_[SG::chan_off(l) + c], v);
+                L.out[q * L.O + o] = v;
+            }
+        }
+    }
+}
+
+template <typename SG, int G>
+__global__ void __launch_bounds__(kTileQ * G)
+k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int K, long long BN, float* dlocs)
+{
+    constexpr int D = SG::D, V = SG::bwd_vec(), CT = SG::ctot();
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float4* s_rec = reinterpret_cast<float4*>(s_raw);
+    __shared__ TileDesc s_desc;
+    __shared__ __align__(8) unsigned long long s_bar;
+    if (*ta.flag != 0) return;
+    const int tid = threadIdx.x, tb = blockIdx.x, b = blockIdx.y;
+    if (tid < 32) reinterpret_cast<int*>(&s_desc)[tid] = reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb)[tid];
+    if (tid == 0) mbar_init(&s_bar, 1);
+    if (tid < V) s_rec[tid * kTileCap] = tid == 0 ? make_float4(1e18f, 1e18f, 1e18f, 0.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    __syncthreads();
+    const float4* planes = reinterpret_cast<const float4*>(rec);
+    if (tid < 32) tile_stage<V>(planes, (size_t)BN, (size_t)b * N, s_desc, s_rec, &s_bar);
+
+    const int ql = tid / G, sub = tid % G;
+    const int m = tb * kTileQ + ql;
+    const bool active = m < N;
+    const size_t q = (size_t)b * N + (active ? m : 0);
+    const SphF sp = {ga.H, ga.invH, ga.H2};
+    float me[V * 4];  // my own record: position, data_l[i], U_l[i]
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const float4 t = planes[(size_t)v * BN + q];
+        me[4 * v] = t.x; me[4 * v + 1] = t.y; me[4 * v + 2] = t.z; me[4 * v + 3] = t.w;
+    }
+    const int cnt = active ? ta.counts[q] : 0;
+    const int nunits = (cnt + kTileUnit - 1) / kTileUnit;
+    const unsigned char* my_units = ta.lists + tile_entry_off(ta.ntb, K, b, tb, ql, 0) + sub * (32 / G);
+    float a_dl[D], a_dd[CT];
+#pragma unroll
+    for (int k = 0; k < D; ++k) a_dl[k] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < CT; ++i) a_dd[i] = 0.0f;
+    mbar_wait(&s_bar, 0);
+
+    auto pair = [&](const float* r) {
+        float disp[D];
+        float d2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            disp[k] = me[k] - r[k];
+            d2 += disp[k] * disp[k];
+        }
+        if (d2 < ga.rad2) {
+            const bool pos = d2 > 0.0f;
+            const float inv = fast_rsqrt(d2);
+            const float d = pos ? d2 * inv : 0.0f;
+            float s[SG::NL], t[SG::NL];
+            layer_scales<SG, true>(ga, sp, d, d2, inv, pos, s, t);
+            float T = 0.0f;
+#pragma unroll
+            for (int l = 0; l < SG::NL; ++l) {
+                float AB = 0.0f;
+#pragma unroll
+                for (int c = 0; c < SG::C(l); ++c) {
+                    // pair (i, j): U_l[i] . data_l[j]   +   pair (j, i): U_l[j] . data_l[i]
+                    AB = fmaf(me[SG::u_off(l) + c], r[SG::data_off(l) + c], AB);
+                    AB = fmaf(r[SG::u_off(l) + c], me[SG::data_off(l) + c], AB);
+                    a_dd[SG::chan_off(l) + c] = fmaf(s[l], r[SG::u_off(l) + c], a_dd[SG::chan_off(l) + c]);
+                }
+                T = fmaf(AB, t[l], T);
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) a_dl[k] = fmaf(T, disp[k], a_dl[k]);
+        }
+    };
+    if (s_desc.total + 1 <= kTileCap) {
+        tile_walk<G>(my_units, nunits, [&](unsigned slot) {
+            float r[V * 4];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float4 t = s_rec[v * kTileCap + slot];
+                r[4 * v] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
+            }
+            pair(r);
+        });
+    } else {
+        tile_walk<G>(my_units, nunits, [&](unsigned slot) {
+            if (slot == 0) return;
+            const size_t j = (size_t)b * N + tile_slot_to_index(s_desc, slot);
+            float r[V * 4];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float4 t = planes[(size_t)v * BN + j];
+                r[4 * v] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
+            }
+            pair(r);
+        });
+    }
+    if (G > 1) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) a_dl[k] = group_sum<G>(a_dl[k]);
+#pragma unroll
+        for (int i = 0; i < CT; ++i) a_dd[i] = group_sum<G>(a_dd[i]);
+    }
+    if (active && sub == 0) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) dlocs[q * D + k] = a_dl[k];
+#pragma unroll
+        for (int l = 0; l < SG::NL; ++l) {
+            if (ga.l[l].ddata) {
+#pragma unroll
+                for (int c = 0; c < SG::C(l); ++c) ga.l[l].ddata[q * SG::C(l) + c] = a_dd[SG::chan_off(l) + c];
+            }
+        }
+    }
+}
+
 // ---- host -------------------------------------------------------------------------------------------
 struct Signature {
     int D, NL;
@@ -518,22 +883,90 @@ static bool make_signature(const float* locs, int D, int nl, const SpnbGroupLaye
     X(2, 2, 0x12u, 0x10u, 0xBBu, 0x0u)                      \
     X(2, 1, 0x2u, 0x0u, 0x1u, 0x0u)
 
+static bool make_tile_args(const void* tiles, int B, int N, int K, TileArgs& ta)
+{
+    if (!tiles) return false;
+    const TileLayout tl = tile_layout(B, N, K);
+    const unsigned char* base = (const unsigned char*)tiles;
+    ta.flag = (const int*)base;
+    ta.descs = (const TileDesc*)(base + tl.desc_off);
+    ta.counts = (const int*)(base + tl.cnt_off);
+    ta.lists = base + tl.list_off;
+    ta.ntb = tl.ntb;
+    return true;
+}
+
+static bool launched(const char* what)
+{
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return true;
+    set_error("convsp group: launch of %s failed: %s", what, cudaGetErrorString(e));
+    return false;
+}
+
+template <typename KernelT>
+static bool allow_smem(KernelT* kernel, size_t bytes)
+{
+    // static + dynamic shared memory above 48 KB needs the opt-in
+    if (bytes + 1024 > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(max dynamic smem %zu): %s", bytes, cudaGetErrorString(e));
+            return false;
+        }
+    }
+    return true;
+}
+
+// With tile lists: pack (layout chosen on the device by the tile flag), the tile kernel (runs when the
+// flag is 0), the list walk (runs when it is not).  Without: pack + list walk.
 template <typename SG>
-static void run_fwd(const float* locs, const float* neighbors, const GroupArgs& ga, int B, int N, int K,
-                    float* rec, cudaStream_t stream)
+static int run_fwd(const float* locs, const float* neighbors, const GroupArgs& ga, int B, int N, int K,
+                   float* rec, const void* tiles, cudaStream_t stream)
 {
     const long long BN = (long long)B * N;
-    k_group_pack<SG, false><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec);
-    k_group_fwd<SG><<<dim3(cdiv((long long)N * SPNB_GROUP_FWD_G, kThreads), B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K);
+    TileArgs ta;
+    const bool tiled = make_tile_args(tiles, B, N, K, ta);
+    const int* tflag = tiled ? ta.flag : nullptr;
+    k_group_pack<SG, false><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec, tflag, nullptr, nullptr);
+    if (!launched("k_group_pack")) return -1;
+    if (tiled) {
+        constexpr int G = SPNB_TILE_FWD_G;
+        const size_t smem = (size_t)SG::fwd_vec() * kTileCap * sizeof(float4);
+        if (!allow_smem(k_tile_fwd<SG, G>, smem)) return -1;
+        k_tile_fwd<SG, G><<<dim3(ta.ntb, B), kTileQ * G, smem, stream>>>(rec, ta, ga, N, K, BN);
+        if (!launched("k_tile_fwd")) return -1;
+    }
+    const int nbx = cdiv((long long)N * SPNB_GROUP_FWD_G, kThreads);
+    if (tiled)
+        k_group_fwd_fallback<SG><<<kFallbackGrid, kThreads, 0, stream>>>(rec, neighbors, ga, N, K, nbx, B, tflag);
+    else
+        k_group_fwd<SG><<<dim3(nbx, B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K);
+    return tiled ? 3 : 2;
 }
 template <typename SG>
-static void run_bwd(const float* locs, const float* neighbors, const GroupArgs& ga, int B, int N, int K,
-                    float* rec, float* dlocs, const int* sym_flag, cudaStream_t stream)
+static int run_bwd(const float* locs, const float* neighbors, const GroupArgs& ga, int B, int N, int K,
+                   float* rec, float* dlocs, const int* sym_flag, const void* tiles, cudaStream_t stream)
 {
     const long long BN = (long long)B * N;
-    k_group_pack<SG, true><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec);
-    k_group_bwd<SG><<<dim3(cdiv((long long)N * SPNB_GROUP_BWD_G, kThreads), B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K,
-                                                                                        dlocs, sym_flag);
+    TileArgs ta;
+    const bool tiled = make_tile_args(tiles, B, N, K, ta);
+    const int* tflag = tiled ? ta.flag : nullptr;
+    k_group_pack<SG, true><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec, tflag, dlocs, sym_flag);
+    if (!launched("k_group_pack")) return -1;
+    if (tiled) {
+        constexpr int G = SPNB_TILE_BWD_G;
+        const size_t smem = (size_t)SG::bwd_vec() * kTileCap * sizeof(float4);
+        if (!allow_smem(k_tile_bwd<SG, G>, smem)) return -1;
+        k_tile_bwd<SG, G><<<dim3(ta.ntb, B), kTileQ * G, smem, stream>>>(rec, ta, ga, N, K, BN, dlocs);
+        if (!launched("k_tile_bwd")) return -1;
+    }
+    const int nbx = cdiv((long long)N * SPNB_GROUP_BWD_G, kThreads);
+    if (tiled)
+        k_group_bwd_fallback<SG><<<kFallbackGrid, kThreads, 0, stream>>>(rec, neighbors, ga, N, K, dlocs, sym_flag, nbx, B, tflag);
+    else
+        k_group_bwd<SG><<<dim3(nbx, B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K, dlocs, sym_flag);
+    return tiled ? 3 : 2;
 }
 
 static size_t record_floats(const Signature& sg, bool bwd)
@@ -566,7 +999,7 @@ size_t spnb_convsp_group_workspace_bytes(const float* locs, int batch_size, int 
 
 int spnb_convsp_group_forward(const float* locs, const float* neighbors, int B, int N, int D, int K,
                               float radius, int nlayers, const SpnbGroupLayer* layers, void* workspace,
-                              size_t workspace_bytes, void* stream_)
+                              size_t workspace_bytes, const void* tile_lists, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     Signature sg;
@@ -594,16 +1027,19 @@ int spnb_convsp_group_forward(const float* locs, const float* neighbors, int B, 
     }
 #define X(DD, NN, CC, SS_, FF, NO)                                                                 \
     if (sg.D == DD && sg.NL == NN && sg.CS == CC && sg.SS == SS_ && sg.FS == FF && sg.NS == NO)    \
-        run_fwd<Sig<DD, NN, CC, SS_, FF, NO>>(locs, neighbors, ga, B, N, K, (float*)workspace, stream);
+        nl = run_fwd<Sig<DD, NN, CC, SS_, FF, NO>>(locs, neighbors, ga, B, N, K, (float*)workspace, tile_lists, stream);
+    int nl = 0;
     SPNB_GROUP_SIGS(X)
 #undef X
-    count_launches(2);
+    if (nl < 0) return 0;
+    count_launches(nl);
     return check_launch("spnb_convsp_group_forward") ? 1 : 0;
 }
 
 int spnb_convsp_group_backward(const float* locs, const float* neighbors, int B, int N, int D, int K,
                                float radius, int nlayers, const SpnbGroupLayer* layers, float* dlocs,
-                               const int* sym_flag, void* workspace, size_t workspace_bytes, void* stream_)
+                               const int* sym_flag, void* workspace, size_t workspace_bytes,
+                               const void* tile_lists, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     Signature sg;
@@ -629,17 +1065,15 @@ int spnb_convsp_group_backward(const float* locs, const float* neighbors, int B,
         set_error("spnb_convsp_group_backward: workspace too small (%zu < %zu)", workspace_bytes, need);
         return 0;
     }
-    // scatter targets start from zero (the gather mode overwrites; which one runs is a device decision)
-    cudaMemsetAsync(dlocs, 0, sizeof(float) * (size_t)B * N * D, stream);
-    for (int l = 0; l < nlayers; ++l)
-        if (layers[l].ddata)
-            cudaMemsetAsync(layers[l].ddata, 0, sizeof(float) * (size_t)B * N * layers[l].nchannels, stream);
+    // (the pack pre-pass zero-fills the scatter targets when the atomics mode is going to run)
 #define X(DD, NN, CC, SS_, FF, NO)                                                                 \
     if (sg.D == DD && sg.NL == NN && sg.CS == CC && sg.SS == SS_ && sg.FS == FF && sg.NS == NO)    \
-        run_bwd<Sig<DD, NN, CC, SS_, FF, NO>>(locs, neighbors, ga, B, N, K, (float*)workspace, dlocs, sym_flag, stream);
+        nl = run_bwd<Sig<DD, NN, CC, SS_, FF, NO>>(locs, neighbors, ga, B, N, K, (float*)workspace, dlocs, sym_flag, tile_lists, stream);
+    int nl = 0;
     SPNB_GROUP_SIGS(X)
 #undef X
-    count_launches(2);
+    if (nl < 0) return 0;
+    count_launches(nl);
     return check_launch("spnb_convsp_group_backward") ? 1 : 0;
 }
 

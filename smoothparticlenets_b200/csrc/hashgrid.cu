@@ -19,6 +19,7 @@
 //    set that is resolved once and staged in shared memory, hits are compacted with ballot/popc so
 //    rows are written coalesced, including the -1 padding.
 #include "spnb_common.cuh"
+#include "tile_lists.cuh"
 
 namespace spnb {
 
@@ -387,6 +388,103 @@ k_table_fill(const uint32_t* __restrict__ keys, const float* __restrict__ grid_d
     if (i == N - 1 && c < (uint32_t)n) ends[(size_t)b * ncells + c] = (float)N;
 }
 
+// ---- tile descriptors (tile_lists.cuh) -------------------------------------------------------------
+// One warp per tile block of kTileQ consecutive sorted queries: the block's cells span the keys
+// [cf, cl]; for every offset o of the leading D-1 grid dimensions its neighbours lie in the cells
+// [cf+o-1, cl+o+1] (a superset: cells that wrap around a grid border only add candidates that fail the
+// distance test or are never referenced).  Each lane turns one such cell interval into a range of the
+// sorted order with two binary searches over the sorted keys; lane 0 sorts and merges the ranges.
+__device__ __forceinline__ int key_lower_bound(const uint32_t* __restrict__ k, int N, long long v)
+{
+    int lo = 0, hi = N;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)k[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+k_tile_ranges(const uint32_t* __restrict__ keys, const float* __restrict__ grid_dims, int N, int D,
+              int ncells, int ntb, TileDesc* __restrict__ descs, int* flag)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tb = blockIdx.x * 8 + warp, b = blockIdx.y;
+    if (tb >= ntb) return;
+    const uint32_t* k = keys + (size_t)b * N;
+    const float* gd = grid_dims + b * D;
+    long long used = 1;
+    for (int d = 0; d < D; ++d) used *= (long long)gd[d];
+    if (used > ncells) used = ncells;
+    const int q0 = tb * kTileQ, q1 = min(q0 + kTileQ, N) - 1;
+    const long long cf = k[q0], cl = k[q1];
+    const int sy = (int)gd[D - 1];
+    const int sx = D >= 3 ? sy * (int)gd[D - 2] : 0;
+    int nrange = 1;
+    for (int d = 1; d < D; ++d) nrange *= 3;
+    int s = 0, e = 0;
+    if (lane < nrange) {
+        long long o = 0;
+        if (D == 2) o = (long long)(lane - 1) * sy;
+        if (D == 3) o = (long long)(lane % 3 - 1) * sy + (long long)(lane / 3 - 1) * sx;
+        long long lo = cf + o - 1, hi = cl + o + 1;
+        if (lo < 0) lo = 0;
+        if (hi > used - 1) hi = used - 1;
+        if (lo <= hi) {
+            s = key_lower_bound(k, N, lo);
+            e = key_lower_bound(k, N, hi + 1);
+        }
+    }
+    int rs[kTileMaxRanges], re[kTileMaxRanges];
+#pragma unroll
+    for (int r = 0; r < kTileMaxRanges; ++r) {
+        rs[r] = __shfl_sync(0xffffffffu, s, r);
+        re[r] = __shfl_sync(0xffffffffu, e, r);
+    }
+    if (lane != 0) return;
+    // insertion sort by start (empty ranges last), then merge overlaps
+    int n = 0;
+    int ss[kTileMaxRanges], ee[kTileMaxRanges];
+    for (int r = 0; r < nrange; ++r) {
+        if (re[r] <= rs[r]) continue;
+        int p = n++;
+        while (p > 0 && ss[p - 1] > rs[r]) {
+            ss[p] = ss[p - 1];
+            ee[p] = ee[p - 1];
+            --p;
+        }
+        ss[p] = rs[r];
+        ee[p] = re[r];
+    }
+    TileDesc d;
+    d.nr = 0;
+    int total = 0;
+    for (int r = 0; r < kTileMaxRanges; ++r) d.start[r] = d.prefix[r] = 0;
+    int cur_s = 0, cur_e = -1;
+    for (int r = 0; r <= n; ++r) {
+        if (r < n && cur_e >= 0 && ss[r] <= cur_e) {
+            if (ee[r] > cur_e) cur_e = ee[r];
+            continue;
+        }
+        if (cur_e >= 0) {
+            d.start[d.nr] = cur_s;
+            d.prefix[d.nr] = total;
+            total += cur_e - cur_s;
+            ++d.nr;
+        }
+        if (r < n) {
+            cur_s = ss[r];
+            cur_e = ee[r];
+        }
+    }
+    d.prefix[d.nr] = total;
+    for (int r = d.nr + 1; r <= kTileMaxRanges; ++r) d.prefix[r] = total;
+    d.total = total;
+    for (int i = 0; i < 11; ++i) d.pad[i] = 0;
+    descs[(size_t)b * ntb + tb] = d;
+}
+
 // ---- neighbour lists -----------------------------------------------------------------------------
 // One warp per kQPW consecutive queries.  Consecutive queries that fall in the same grid cell (all of
 // them, when the queries are the cell-sorted particles themselves) share one candidate set: the
@@ -399,14 +497,16 @@ k_table_fill(const uint32_t* __restrict__ keys, const float* __restrict__ grid_d
 constexpr int kQPW = 8;          // queries per warp
 constexpr int kCollideWarps = 8;  // warps per block
 
-template <int DT>
+template <int DT, bool TILES>
 __global__ void __launch_bounds__(kCollideWarps * 32)
 k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
           const float* __restrict__ low, const float* __restrict__ grid_dims,
           const float* __restrict__ starts, const float* __restrict__ ends,
           float* __restrict__ coll, int M, int N, int ndims, int K, int ncells, float edge, float r2,
-          int include_self, int* trunc_flag)
+          int include_self, int* trunc_flag, const TileDesc* __restrict__ descs, int* __restrict__ tcounts,
+          unsigned short* __restrict__ tlists, int ntb, int* tile_flag)
 {
+    static_assert(!TILES || kCollideWarps * kQPW == kTileQ, "a collide block is one tile block");
     constexpr int MD = DT > 0 ? DT : SPNB_MAXD;
     constexpr int CM = DT > 0 ? 256 : 64;  // staged candidates per window
     const int D = DT > 0 ? DT : ndims;
@@ -415,9 +515,18 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
     __shared__ int s_idx[kCollideWarps][CM];
     __shared__ float s_y[kCollideWarps][MD][CM];
     __shared__ int s_found[kCollideWarps][kQPW];
+    __shared__ unsigned short s_loc[kCollideWarps][TILES ? CM : 1];
+    __shared__ TileDesc s_desc;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
+    if (TILES) {
+        // the compact lists of this block's 64 queries index into the tile described by s_desc
+        if (threadIdx.x < (int)(sizeof(TileDesc) / sizeof(int)))
+            reinterpret_cast<int*>(&s_desc)[threadIdx.x] =
+                reinterpret_cast<const int*>(descs + (size_t)b * ntb + blockIdx.x)[threadIdx.x];
+        __syncthreads();
+    }
     const int q0 = (blockIdx.x * kCollideWarps + warp) * kQPW;
     if (q0 >= M) return;
     const int nq = min(kQPW, M - q0);
@@ -432,6 +541,7 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
 #pragma unroll
     for (int k = 0; k < D; ++k) total_cells *= 3;
     bool truncated = false;
+    bool tile_wide = false;
 
     int qi = 0;
     while (qi < nq) {
@@ -494,6 +604,14 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
                         if (s_off[warp][c + s] <= tt) c += s;
                     const int idx = s_start[warp][c] + (tt - s_off[warp][c]);
                     s_idx[warp][t] = idx;
+                    if (TILES) {
+                        int loc = 0;  // slot of particle idx in the staged tile (ranges ascend)
+#pragma unroll
+                        for (int r = 0; r < kTileMaxRanges; ++r)
+                            if (r < s_desc.nr && idx >= s_desc.start[r]) loc = 1 + s_desc.prefix[r] + idx - s_desc.start[r];
+                        if (loc > 0xffff) tile_wide = true;  // slot does not fit 16 bits: sidecar unusable
+                        s_loc[warp][t] = (unsigned short)loc;
+                    }
 #pragma unroll
                     for (int k = 0; k < D; ++k) s_y[warp][k][t] = sl[(size_t)idx * D + k];
                 }
@@ -506,6 +624,8 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
 #pragma unroll
                     for (int k = 0; k < D; ++k) x[k] = sq[(qi + r) * D + k];
                     float* row = rows + (size_t)(qi + r) * K;
+                    unsigned short* trow = nullptr;
+                    if (TILES) trow = tlists + tile_entry_off(ntb, K, b, blockIdx.x, warp * kQPW + qi + r, 0) / 2;
                     for (int base = 0; base < wn && found < K; base += 32) {
                         const int t = base + lane;
                         bool hit = false;
@@ -522,7 +642,10 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
                         }
                         const unsigned m = __ballot_sync(0xffffffffu, hit);
                         const int pos = found + __popc(m & lanemask_lt());
-                        if (hit && pos < K) row[pos] = (float)idx;
+                        if (hit && pos < K) {
+                            row[pos] = (float)idx;
+                            if (TILES) trow[(pos >> 4) * 128 + (pos & 15)] = s_loc[warp][t];
+                        }
                         found += __popc(m);
                     }
                     if (lane == 0) s_found[warp][r] = found;
@@ -539,11 +662,20 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
             }
             float* row = rows + (size_t)(qi + r) * K;
             for (int p = found + lane; p < K; p += 32) row[p] = -1.0f;
+            if (TILES) {
+                // sentinel-fill the tail of the last unit, publish the length
+                unsigned short* trow = tlists + tile_entry_off(ntb, K, b, blockIdx.x, warp * kQPW + qi + r, 0) / 2;
+                const int p = found + lane;
+                if (p < ((found + kTileUnit - 1) & ~(kTileUnit - 1))) trow[(p >> 4) * 128 + (p & 15)] = 0;
+                if (lane == 0) tcounts[(size_t)b * N + q0 + qi + r] = found;
+            }
         }
         __syncwarp();
         qi += run;
     }
     if (truncated && trunc_flag && lane == 0) atomicOr(trunc_flag, 1);
+    if (TILES && truncated && lane == 0) atomicOr(tile_flag, 1);
+    if (TILES && tile_wide) atomicOr(tile_flag, 2);
 }
 
 // ---- launch helpers --------------------------------------------------------------------------------
@@ -701,11 +833,17 @@ int spnb_reorder_data(const float* locs, const float* data, const float* idxs, f
     return check_launch("spnb_reorder_data") ? 1 : 0;
 }
 
-int spnb_compute_collisions(const float* qlocs, const float* locs, const float* low,
-                            const float* grid_dims, const float* cellIDs, float* cellStarts,
-                            float* cellEnds, float* collisions, int B, int M, int N, int D, int K,
-                            int ncells, float cellEdge, float radius, int include_self,
-                            int* trunc_flag, void* stream_)
+size_t spnb_tile_lists_bytes(int batch_size, int N, int ndims, int max_collisions)
+{
+    if (batch_size <= 0 || !tile_lists_supported(N, ndims, max_collisions)) return 0;
+    return tile_layout(batch_size, N, max_collisions).total;
+}
+
+static int collide_impl(const float* qlocs, const float* locs, const float* low,
+                        const float* grid_dims, const float* cellIDs, float* cellStarts,
+                        float* cellEnds, float* collisions, int B, int M, int N, int D, int K,
+                        int ncells, float cellEdge, float radius, int include_self,
+                        int* trunc_flag, void* tiles, size_t tiles_bytes, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!valid_common(B, N, D, "spnb_compute_collisions")) return 0;
@@ -722,10 +860,42 @@ int spnb_compute_collisions(const float* qlocs, const float* locs, const float* 
                                                             cellStarts, cellEnds, N, D, ncells);
     const float r2 = radius * radius;
     const dim3 blocks(cdiv(M, kCollideWarps * kQPW), B);
-#define SPNB_COLLIDE(DT)                                                                          \
-    k_collide<DT><<<blocks, kCollideWarps * 32, 0, stream>>>(                                      \
+    if (tiles) {
+        if (qlocs != locs || M != N || !tile_lists_supported(N, D, K)) {
+            set_error("spnb_compute_collisions_tiled: needs qlocs == locs and ndims <= %d, max_collisions %% %d == 0",
+                      kTileMaxNdim, kTileUnit);
+            return 0;
+        }
+        const TileLayout tl = tile_layout(B, N, K);
+        if (tiles_bytes < tl.total) {
+            set_error("spnb_compute_collisions_tiled: tile buffer too small (%zu < %zu)", tiles_bytes, tl.total);
+            return 0;
+        }
+        char* tb = (char*)tiles;
+        int* tflag = (int*)tb;
+        TileDesc* descs = (TileDesc*)(tb + tl.desc_off);
+        int* tcounts = (int*)(tb + tl.cnt_off);
+        unsigned short* tlists = (unsigned short*)(tb + tl.list_off);
+        cudaMemsetAsync(tflag, 0, 128, stream);
+        k_tile_ranges<<<dim3(cdiv(tl.ntb, 8), B), 256, 0, stream>>>((const uint32_t*)cellIDs, grid_dims, N, D,
+                                                                    ncells, tl.ntb, descs, tflag);
+#define SPNB_COLLIDE_T(DT)                                                                        \
+    k_collide<DT, true><<<blocks, kCollideWarps * 32, 0, stream>>>(                                \
         qlocs, locs, low, grid_dims, cellStarts, cellEnds, collisions, M, N, D, K, ncells, cellEdge, \
-        r2, include_self, trunc_flag)
+        r2, include_self, trunc_flag, descs, tcounts, tlists, tl.ntb, tflag)
+        switch (D) {
+        case 1: SPNB_COLLIDE_T(1); break;
+        case 2: SPNB_COLLIDE_T(2); break;
+        default: SPNB_COLLIDE_T(3); break;
+        }
+#undef SPNB_COLLIDE_T
+        count_launches(4);
+        return check_launch("spnb_compute_collisions_tiled") ? 1 : 0;
+    }
+#define SPNB_COLLIDE(DT)                                                                          \
+    k_collide<DT, false><<<blocks, kCollideWarps * 32, 0, stream>>>(                               \
+        qlocs, locs, low, grid_dims, cellStarts, cellEnds, collisions, M, N, D, K, ncells, cellEdge, \
+        r2, include_self, trunc_flag, nullptr, nullptr, nullptr, 0, nullptr)
     switch (D) {
     case 1: SPNB_COLLIDE(1); break;
     case 2: SPNB_COLLIDE(2); break;
@@ -735,6 +905,30 @@ int spnb_compute_collisions(const float* qlocs, const float* locs, const float* 
 #undef SPNB_COLLIDE
     count_launches(3);
     return check_launch("spnb_compute_collisions") ? 1 : 0;
+}
+
+int spnb_compute_collisions(const float* qlocs, const float* locs, const float* low,
+                            const float* grid_dims, const float* cellIDs, float* cellStarts,
+                            float* cellEnds, float* collisions, int B, int M, int N, int D, int K,
+                            int ncells, float cellEdge, float radius, int include_self,
+                            int* trunc_flag, void* stream_)
+{
+    return collide_impl(qlocs, locs, low, grid_dims, cellIDs, cellStarts, cellEnds, collisions, B, M, N, D, K,
+                        ncells, cellEdge, radius, include_self, trunc_flag, nullptr, 0, stream_);
+}
+
+int spnb_compute_collisions_tiled(const float* qlocs, const float* locs, const float* low,
+                                  const float* grid_dims, const float* cellIDs, float* cellStarts,
+                                  float* cellEnds, float* collisions, int B, int M, int N, int D, int K,
+                                  int ncells, float cellEdge, float radius, int include_self,
+                                  int* trunc_flag, void* tile_lists, size_t tile_lists_bytes, void* stream_)
+{
+    if (!tile_lists) {
+        set_error("spnb_compute_collisions_tiled: null tile buffer");
+        return 0;
+    }
+    return collide_impl(qlocs, locs, low, grid_dims, cellIDs, cellStarts, cellEnds, collisions, B, M, N, D, K,
+                        ncells, cellEdge, radius, include_self, trunc_flag, tile_lists, tile_lists_bytes, stream_);
 }
 
 }  // extern "C"

@@ -167,13 +167,13 @@ __device__ __forceinline__ void walk_rows(const float* __restrict__ warp_rows, i
 #ifndef SPNB_PREFETCH_BLOCKS
 #define SPNB_PREFETCH_BLOCKS (148 * 16)
 #endif
+// (bx, by) of (nbx, gridDim.y-equivalent) is the logical block; by default the launch's own block index.
 __device__ __forceinline__ void prefetch_rows_ahead(const float* __restrict__ neighbors, int M, int K,
-                                                    int rows_per_block, int lines)
+                                                    int rows_per_block, int lines, int bx, int by, int nbx, int nby)
 {
-    const long long nblocks = (long long)gridDim.x * gridDim.y;
-    const long long lb = (long long)blockIdx.y * gridDim.x + blockIdx.x + SPNB_PREFETCH_BLOCKS;
-    if (lb >= nblocks) return;
-    const int b2 = (int)(lb / gridDim.x), x2 = (int)(lb % gridDim.x);
+    const long long lb = (long long)by * nbx + bx + SPNB_PREFETCH_BLOCKS;
+    if (lb >= (long long)nbx * nby) return;
+    const int b2 = (int)(lb / nbx), x2 = (int)(lb % nbx);
     const int t = threadIdx.x;
     const int row = t / lines, line = t % lines;
     if (row >= rows_per_block) return;
@@ -181,6 +181,11 @@ __device__ __forceinline__ void prefetch_rows_ahead(const float* __restrict__ ne
     if (m >= M || line * 32 >= K) return;
     const float* p = neighbors + ((size_t)b2 * M + m) * K + line * 32;
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void prefetch_rows_ahead(const float* __restrict__ neighbors, int M, int K,
+                                                    int rows_per_block, int lines)
+{
+    prefetch_rows_ahead(neighbors, M, K, rows_per_block, lines, blockIdx.x, blockIdx.y, gridDim.x, gridDim.y);
 }
 
 // Sum over the G lanes of a group (all lanes receive the total).

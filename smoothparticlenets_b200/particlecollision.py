@@ -7,6 +7,7 @@ semantics (only the reorder pass-through carries gradients, ParticleCollision.py
 cell table and neighbour lists run without a host synchronisation.
 """
 import numbers  # noqa: F401
+import os
 
 import torch
 
@@ -92,6 +93,9 @@ class ParticleCollision(torch.nn.Module):
         self.max_collisions = ec.check_conditions(max_collisions, "max_collisions", "%s > 0",
                                                   "isinstance(%s, numbers.Integral)")
         self.include_self = 1 if include_self else 0
+        # extension (not in the reference): also emit the compact tile lists that ConvSPGroup consumes;
+        # the float neighbour tensor that is returned is unaffected
+        self.tile_lists = os.environ.get("SPNB_TILE_LISTS", "1") != "0"
         self.radixsort_buffer_size = -1
         # Same buffer names as the reference (ParticleCollision.py:97-100) so state_dicts load.
         # cellStarts/cellEnds are allocated lazily at [B, max_grid_dim**ndim] on first use.
@@ -182,16 +186,31 @@ class ParticleCollision(torch.nn.Module):
             neighbors = torch.empty(batch_size, M, self.max_collisions, device=dev,
                                     dtype=torch.float32)
             trunc = torch.zeros(1, device=dev, dtype=torch.int32)
-            nat.check(L.spnb_compute_collisions(
-                nat.ptr(q), nat.ptr(locs.detach()), nat.ptr(lower_bounds), nat.ptr(grid_dims),
-                nat.ptr(cellIDs), nat.ptr(cellStarts), nat.ptr(cellEnds), nat.ptr(neighbors),
-                batch_size, M, N, D, self.max_collisions, ncells, float(self.radius),
-                float(self.radius), self.include_self, nat.ptr(trunc), nat.stream()),
-                "spnb_compute_collisions")
+            tiles = None
+            tile_bytes = (L.spnb_tile_lists_bytes(batch_size, N, D, self.max_collisions)
+                          if qlocs is None and self.tile_lists else 0)
+            if tile_bytes > 0:
+                # compact sidecar of the same lists (csrc/tile_lists.cuh) for the ConvSPGroup kernels
+                tiles = torch.empty(tile_bytes, device=dev, dtype=torch.uint8)
+                ls = locs.detach()
+                nat.check(L.spnb_compute_collisions_tiled(
+                    nat.ptr(ls), nat.ptr(ls), nat.ptr(lower_bounds), nat.ptr(grid_dims),
+                    nat.ptr(cellIDs), nat.ptr(cellStarts), nat.ptr(cellEnds), nat.ptr(neighbors),
+                    batch_size, M, N, D, self.max_collisions, ncells, float(self.radius),
+                    float(self.radius), self.include_self, nat.ptr(trunc), nat.ptr(tiles), tile_bytes,
+                    nat.stream()), "spnb_compute_collisions_tiled")
+            else:
+                nat.check(L.spnb_compute_collisions(
+                    nat.ptr(q), nat.ptr(locs.detach()), nat.ptr(lower_bounds), nat.ptr(grid_dims),
+                    nat.ptr(cellIDs), nat.ptr(cellStarts), nat.ptr(cellEnds), nat.ptr(neighbors),
+                    batch_size, M, N, D, self.max_collisions, ncells, float(self.radius),
+                    float(self.radius), self.include_self, nat.ptr(trunc), nat.stream()),
+                    "spnb_compute_collisions")
         if qlocs is None:
             # Lists built with the particles as their own queries are symmetric unless one was cut
             # at max_collisions; ConvSP's backward uses this to avoid atomics.
             neighbors._spnb_sym_flag = trunc
+            neighbors._spnb_tiles = tiles
         self.last_lower_bounds = lower_bounds
         self.last_grid_dims = grid_dims
         if has_data:

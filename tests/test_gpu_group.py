@@ -28,13 +28,16 @@ def close(a, b, what, k=4):
 
 
 @pytest.mark.parametrize("D", [3, 2])
-@pytest.mark.parametrize("mode", ["sym", "atomic"])
+@pytest.mark.parametrize("mode", ["tile", "sym", "atomic"])
 def test_group_matches_per_layer(spn, D, mode):
     B, N = 2, 700
     r = cases.rng(3)
     locs, vel, L = cases.fluid_cloud(5, B, N, D=D, density=7640.0 if D == 3 else 600.0)
     coll = spn.ParticleCollision(D, 0.1, include_self=False).cuda()
+    coll.tile_lists = mode == "tile"  # tile: compact tile lists; sym/atomic: walk of the float lists
     sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
+    if mode == "tile":
+        assert int(nb._spnb_tiles[:4].view(torch.int32).item()) == 0, "tile lists usable"
     if mode == "atomic":
         nb = nb.clone()  # drops the symmetry tag -> scatter path
     ones = torch.ones(B, N, 1, device="cuda")
@@ -58,7 +61,8 @@ def test_group_matches_per_layer(spn, D, mode):
             outs = group(l, datas, nb) if which == "fused" else tuple(
                 lay(l, d, nb) for lay, d in zip(layers, datas))
             if which == "fused":  # pack + one walk, not one launch per layer
-                assert nat.lib().spnb_launch_count() - n0 == 2, "group %s did not take the fused path" % name
+                want = 3 if mode == "tile" else 2  # pack + (tile kernel) + list walk
+                assert nat.lib().spnb_launch_count() - n0 == want, "group %s did not take the fused path" % name
             if gos is None:
                 gos = [torch.rand_like(o) for o in outs]
             torch.autograd.backward(outs, gos)
@@ -103,3 +107,59 @@ def test_fused_fluid_step_matches_layerwise(spn):
         # 3 solver iterations chain ~30 fp32 reductions: compare at 1e-4 of the tensor's scale
         scale = float(b.abs().max())
         assert float((a - b).abs().max()) <= 1e-4 * scale, (nm, float((a - b).abs().max()), scale)
+
+
+def test_group_tile_flag_falls_back_on_device(spn):
+    """Lists cut at max_collisions raise the tile flag; the group kernels then run from the float lists,
+    decided on the device, with the same results."""
+    B, N, D = 1, 1500, 3
+    r = cases.rng(4)
+    locs = (r.rand(B, N, D) * 0.25).astype(np.float32)  # 1500 particles within 2-3 cells per axis
+    vel = r.rand(B, N, D).astype(np.float32)
+    layers = make_layers(spn, D, [("spiky", D, False), ("spiky", 1, False)], r)
+    group = spn.ConvSPGroup(layers)
+    res = {}
+    for tiles_on in (True, False):
+        coll = spn.ParticleCollision(D, 0.1, max_collisions=128, include_self=False).cuda()
+        coll.tile_lists = tiles_on
+        sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
+        if tiles_on:
+            assert int(nb._spnb_tiles[:4].view(torch.int32).item()) != 0
+        l = sl.detach().clone().requires_grad_(True)
+        ones = torch.ones(B, N, 1, device="cuda")
+        outs = group(l, [sv, ones], nb)
+        torch.autograd.backward(outs, [torch.ones_like(o) for o in outs])
+        res[tiles_on] = ([o.detach() for o in outs], l.grad.clone())
+    for a, b in zip(res[True][0], res[False][0]):
+        assert torch.equal(a, b)
+    # lists are cut at K here, so the backward is the atomics mode in both runs: order-dependent rounding
+    close(res[True][1], res[False][1], "locs.grad", k=64)
+
+
+def test_group_oversized_tiles_gather_from_global(spn):
+    """Tiles with more records than the staging capacity (dense clump, lists not cut) are processed by the
+    same kernels through the slot -> index table; results must match the float-list walk."""
+    from smoothparticlenets_b200 import tile_lists as tl
+    B, N, D, K = 1, 3000, 3, 256
+    r = cases.rng(8)
+    locs = (r.rand(B, N, D) * 0.5).astype(np.float32)
+    vel = r.rand(B, N, D).astype(np.float32)
+    layers = make_layers(spn, D, [("spiky", D, False), ("spiky", 1, False)], r)
+    group = spn.ConvSPGroup(layers)
+    res = {}
+    for tiles_on in (True, False):
+        coll = spn.ParticleCollision(D, 0.1, max_collisions=K, include_self=False).cuda()
+        coll.tile_lists = tiles_on
+        sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
+        assert int(nb._spnb_sym_flag.item()) == 0
+        if tiles_on:
+            flag, counts, dec, max_total = tl.decode(nb._spnb_tiles, B, N, K)
+            assert flag == 0 and max_total + 1 > tl.TILE_CAP
+        l = sl.detach().clone().requires_grad_(True)
+        ones = torch.ones(B, N, 1, device="cuda")
+        outs = group(l, [sv, ones], nb)
+        torch.autograd.backward(outs, [torch.ones_like(o) for o in outs])
+        res[tiles_on] = ([o.detach() for o in outs], l.grad.clone())
+    for i, (a, b) in enumerate(zip(res[True][0], res[False][0])):
+        close(a, b, "layer %d forward" % i)
+    close(res[True][1], res[False][1], "locs.grad", k=16)

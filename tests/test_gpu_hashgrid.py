@@ -172,3 +172,70 @@ def test_full_size_properties(spn):
     deg_in = torch.zeros(N, device="cuda", dtype=torch.long).index_add_(
         0, j[valid], torch.ones(int(valid.sum()), device="cuda", dtype=torch.long))
     assert torch.equal(deg_in, deg_out)
+
+
+TILE_CASES = [
+    # B, N, D, extent, radius, K, include_self, density
+    (2, 1000, 3, 1.0, 0.1, 128, 0),
+    (3, 777, 2, 1.0, 0.07, 64, 1),
+    (2, 300, 1, 2.0, 0.02, 32, 0),
+    (1, 5000, 3, 1.0, 0.05, 128, 1),
+    (2, 64, 3, 0.3, 0.1, 16, 1),      # K reached: lists cut, flag bit 0
+    (1, 4099, 3, 4.0, 0.03, 128, 0),  # border cells hold many particles (G = 16 clamps)
+]
+
+
+@pytest.mark.parametrize("B,N,D,extent,radius,K,include_self", TILE_CASES)
+def test_tile_lists_describe_the_same_lists(spn, B, N, D, extent, radius, K, include_self):
+    """The compact sidecar (csrc/tile_lists.cuh) must hold exactly the float lists: same entries, same
+    order, same truncation; every entry must resolve inside its tile's staged ranges."""
+    from smoothparticlenets_b200 import tile_lists as tl
+    locs, _, _ = cases.collision_case(11, B=B, N=N, M=1, D=D, C=1, extent=extent)
+    G = 16 if extent > 2.0 and D == 3 else 96
+    coll = spn.ParticleCollision(D, radius, max_grid_dim=G, max_collisions=K, include_self=bool(include_self)).cuda()
+    sl, idxs, nb = coll(gu.dev(locs))
+    tiles = nb._spnb_tiles
+    assert tiles is not None and tiles.dtype == torch.uint8
+    flag, counts, dec, max_total = tl.decode(tiles, B, N, K)
+    nbh = gu.host(nb).astype(np.int64)
+    want_cnt = (nbh >= 0).sum(2)
+    assert np.array_equal(counts, want_cnt), "list lengths"
+    truncated = bool((nbh[..., K - 1] >= 0).any())
+    assert bool(flag & 1) == truncated, "truncation bit of the tile flag"
+    assert not (flag & 2), "16-bit slots suffice"
+    assert np.array_equal(dec, nbh), "decoded tile lists == float lists"
+    # the plain entry point writes the same float rows
+    coll2 = spn.ParticleCollision(D, radius, max_grid_dim=G, max_collisions=K, include_self=bool(include_self)).cuda()
+    coll2.tile_lists = False
+    sl2, idxs2, nb2 = coll2(gu.dev(locs))
+    assert getattr(nb2, "_spnb_tiles", None) is None
+    assert torch.equal(nb, nb2) and torch.equal(idxs, idxs2)
+
+
+def test_tile_lists_full_size(spn):
+    """c2 size: decode a sample of tile blocks and compare with the float rows; flag must be clear."""
+    from smoothparticlenets_b200 import tile_lists as tl
+    B, N, R, K = 8, 65536, 0.1, 128
+    locs, vel, L = cases.fluid_cloud(0, B, N)
+    coll = spn.ParticleCollision(3, R, max_collisions=K, include_self=False).cuda()
+    sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
+    tiles = nb._spnb_tiles
+    assert int(tiles[:4].view(torch.int32).item()) == 0
+    lay = tl.layout(B, N, K)
+    raw = tiles.cpu().numpy()
+    desc = raw[lay["desc_off"]:lay["cnt_off"]].view(np.int32).reshape(B, lay["ntb"], tl.DESC_INTS)
+    totals = desc[:, :, 1]
+    assert totals.min() > 0
+    assert (totals + 1 > tl.TILE_CAP).mean() < 0.01, "tiles that do not fit the staging capacity are rare"
+    counts = raw[lay["cnt_off"]:lay["cnt_off"] + 4 * B * N].view(np.int32).reshape(B, N)
+    assert np.array_equal(counts, gu.host((nb >= 0).sum(2)))
+    # decode scene 5 only (python loop): slice a one-scene view of the buffer
+    b = 5
+    one = np.concatenate([
+        raw[:128], desc[b].reshape(-1).view(np.uint8),
+        np.zeros(tl.layout(1, N, K)["list_off"] - tl.layout(1, N, K)["cnt_off"], np.uint8),
+        raw[lay["list_off"] + b * lay["ntb"] * tl.TILE_Q * K * 2: lay["list_off"] + (b + 1) * lay["ntb"] * tl.TILE_Q * K * 2]])
+    l1 = tl.layout(1, N, K)
+    one[l1["cnt_off"]:l1["cnt_off"] + 4 * N] = counts[b].view(np.uint8)
+    flag, c1, dec, _ = tl.decode(one, 1, N, K)
+    assert np.array_equal(dec[0], gu.host(nb[b]).astype(np.int64))

@@ -128,6 +128,38 @@ def main():
         "gC_fwd": (group_fwd(model_f.group_c, mkC), P * fb(3, 3)),
         "gC_fb": (group_fb(model_f.group_c, mkC), P * (fb(3, 3) + bb(3, 3))),
     }
+    # the group ops called directly through the C ABI (pack + tile kernel + fallback), no autograd around them
+    from smoothparticlenets_b200 import convsp_group as cg
+    tiles = getattr(nb, "_spnb_tiles", None)
+    if os.environ.get("SPNB_MB_NOTILES"):
+        tiles = None
+
+    def direct(group, datas):
+        layers = list(group.layers)
+        cfg = tuple((l.kernel_fn, l.dis_norm, l.nchannels, l.nkernels) for l in layers)
+        ws_ = [l.weight for l in layers]
+        outs = [torch.empty(B, N, c[3], device="cuda") for c in cfg]
+        gos = [torch.rand(B, N, c[3], device="cuda") for c in cfg]
+        dds = [torch.empty_like(d) if d is not ones else None for d in datas]
+        dl = torch.empty_like(sl)
+        afw = cg._layer_array(sl, datas, ws_, [l.bias for l in layers], cfg, outs=outs)
+        abw = cg._layer_array(sl, datas, ws_, None, cfg, gos=gos, ddatas=dds)
+        wf = L.spnb_convsp_group_workspace_bytes(nat.ptr(sl), B, N, D, float(R), len(cfg), afw, 0)
+        wb = L.spnb_convsp_group_workspace_bytes(nat.ptr(sl), B, N, D, float(R), len(cfg), abw, 1)
+        wsf, wsb = torch.empty(wf // 4 + 1, device="cuda"), torch.empty(wb // 4 + 1, device="cuda")
+        keep = (outs, gos, dds, dl, afw, abw, wsf, wsb, datas)
+        f = lambda: (keep, L.spnb_convsp_group_forward(nat.ptr(sl), nat.ptr(nb), B, N, D, K, float(R), len(cfg), afw,
+                                                       nat.ptr(wsf), wf, nat.ptr(tiles), nat.stream()))
+        g = lambda: (keep, L.spnb_convsp_group_backward(nat.ptr(sl), nat.ptr(nb), B, N, D, K, float(R), len(cfg), abw,
+                                                        nat.ptr(dl), nat.ptr(flag), nat.ptr(wsb), wb, nat.ptr(tiles),
+                                                        nat.stream()))
+        eq_f = P * sum(fb(c[2], c[3]) for c in cfg)
+        eq_b = P * sum(bb(c[2], c[3]) for c in cfg)
+        return (f, eq_f), (g, eq_b)
+
+    for nm, grp, datas in (("A", model_f.group_a, mkA(sl)), ("B", model_f.group_b, mkB(sl)),
+                           ("C", model_f.group_c, mkC(sl)), ("V", model_f.group_v, mkV(sl))):
+        table["k%s_f" % nm], table["k%s_b" % nm] = direct(grp, datas)
     if "wide" in only:
         # config 3: 64 -> 64, kernel_size 5, collision radius 0.2 (n-bar ~ 63), 16384 queries of a 1M scene
         import numpy as np
