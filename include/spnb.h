@@ -80,21 +80,21 @@ int spnb_compute_collisions(const float* qlocs, const float* locs, const float* 
                             int include_self, int* trunc_flag, void* stream);
 
 /* Opt-in compact form of the same lists ("tile lists"; layout in
- * smoothparticlenets_b200/csrc/tile_lists.cuh): 16-bit entries that index per-64-query tiles of the
- * sorted order which the ConvSP group kernels stage into shared memory with TMA bulk copies.
- * spnb_tile_lists_bytes() is the device buffer size (0: these sizes are not supported -- needs
- * ndims <= 3 and max_collisions a multiple of 16).  spnb_compute_collisions_tiled() does everything
- * spnb_compute_collisions() does (collisions is filled exactly the same) and fills tile_lists too; it
- * requires the particles to be their own queries (qlocs == locs, M == N).  The first int of the
- * buffer is a device-side flag: non-zero = unusable for this call (a list hit max_collisions or a tile
- * overflowed); consumers test it on the device and fall back to the float lists. */
+ * smoothparticlenets_b200/csrc/tile_lists.cuh): per 64 consecutive queries the ranges of the sorted
+ * order that hold their neighbours (a "tile", staged into shared memory by the ConvSP group kernels with
+ * TMA bulk copies) and 16-bit lists of tile slots.  spnb_tile_lists_bytes() is the device buffer size
+ * (0: these sizes are not supported -- needs ndims <= 3 and max_collisions a multiple of 16).  spnb_build_tile_lists() derives the
+ * buffer from what spnb_hashgrid_order() and spnb_compute_collisions() produced for the particles as
+ * their own queries (cellIDs = sorted keys, cellStarts/cellEnds = the cell table, may both be NULL,
+ * collisions = [batch_size, N, max_collisions]).  The first int
+ * of the buffer is a device-side flag: non-zero = unusable for this call (a list is full / was cut at
+ * max_collisions, or a tile exceeds the format's capacities); consumers test it on the device and fall
+ * back to the float lists. */
 size_t spnb_tile_lists_bytes(int batch_size, int N, int ndims, int max_collisions);
-int spnb_compute_collisions_tiled(const float* qlocs, const float* locs, const float* low,
-                                  const float* grid_dims, const float* cellIDs, float* cellStarts,
-                                  float* cellEnds, float* collisions, int batch_size, int M, int N,
-                                  int ndims, int max_collisions, int ncells, float cellEdge,
-                                  float radius, int include_self, int* trunc_flag, void* tile_lists,
-                                  size_t tile_lists_bytes, void* stream);
+int spnb_build_tile_lists(const float* cellIDs, const float* grid_dims, const float* cellStarts,
+                          const float* cellEnds, const float* collisions, int batch_size, int N,
+                          int ndims, int max_collisions, int ncells, void* tile_lists,
+                          size_t tile_lists_bytes, void* stream);
 
 /* Row permutation.  Replaces cuda_reorder_data (gpu_kernels.h:97-111).
  *   reverse == 0: nlocs[b,i] = locs[b,idxs[b,i]];  reverse != 0: nlocs[b,idxs[b,i]] = locs[b,i];
@@ -158,7 +158,7 @@ typedef struct SpnbGroupLayer {
     int nchannels, nkernels, kernel_fn, dis_norm;
 } SpnbGroupLayer;
 
-/* tile_lists: NULL, or the buffer spnb_compute_collisions_tiled() filled for these neighbors (same
+/* tile_lists: NULL, or the buffer spnb_build_tile_lists() filled for these neighbors (same
  * batch_size, N, max_neighbors): the group then runs from the compact lists when their flag allows. */
 size_t spnb_convsp_group_workspace_bytes(const float* locs, int batch_size, int N, int ndims, float radius,
                                          int nlayers, const SpnbGroupLayer* layers, int backward);

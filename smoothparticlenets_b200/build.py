@@ -15,7 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
-LIB_PATH = os.path.join(HERE, "libspnb.so")
+# SPNB_LIB: build/load a variant library under another name (tuning sweeps prebuilt before a GPU session)
+LIB_PATH = os.environ.get("SPNB_LIB") or os.path.join(HERE, "libspnb.so")
 SOURCES = ["common.cu", "hashgrid.cu", "convsp.cu", "convsp_small.cu", "convsp_group.cu", "convsp_wide.cu", "convsdf.cu"]
 
 NVCC_FLAGS = [

@@ -50,11 +50,13 @@ constexpr int kThreads = 128;
 #define SPNB_GROUP_BWD_U 1
 #endif
 // tile-list kernels (tile_lists.cuh): lanes per query
+// (measured, tools/tune_tile.sh: one lane per query when the record is a single float4, two when the
+// gather needs two LDS.128; four for the backward records)
 #ifndef SPNB_TILE_FWD_G
-#define SPNB_TILE_FWD_G 1
+#define SPNB_TILE_FWD_G 0  // 0 = by record width
 #endif
 #ifndef SPNB_TILE_BWD_G
-#define SPNB_TILE_BWD_G 2
+#define SPNB_TILE_BWD_G 4
 #endif
 constexpr int kMaxLayers = 6;
 constexpr int kFallbackGrid = 148 * 4;  // blocks of the strided list-walk fallback of a tiled call
@@ -162,10 +164,10 @@ __device__ __forceinline__ float sph_fast(int e, float d, float d2, float c, con
     case E_D_INDIRECT: return -1.0f;
     case E_CONSTANT:  return 1.0f;
     case E_D_CONSTANT: return 0.0f;
-    case E_SPIKY:     { const float q = 1.0f - d * p.invH; return c * q * q; }
-    case E_DSPIKY:    return c * (1.0f - d * p.invH);
+    case E_SPIKY:     { const float q = fmaf(-d, p.invH, 1.0f); return c * q * q; }
+    case E_DSPIKY:    return c * fmaf(-d, p.invH, 1.0f);
     case E_D_DSPIKY:  return c;
-    case E_COHESION:  { const float t = d * p.invH; return (7.0f - 6.0f * t) * t * t - 1.0f; }
+    case E_COHESION:  { const float t = d * p.invH; return fmaf(fmaf(-6.0f, t, 7.0f) * t, t, -1.0f); }
     case E_D_COHESION: return 2.0f * d * (7.0f * p.H - 9.0f * d) * (p.invH * p.invH * p.invH);
     case E_SIGMOID:   return 1.0f / (1.0f + expf((d - 0.2f * p.H) * 20.0f * p.invH));
     case E_D_SIGMOID: { const float ex = expf((d - 0.2f * p.H) * 20.0f * p.invH);
@@ -931,7 +933,7 @@ static int run_fwd(const float* locs, const float* neighbors, const GroupArgs& g
     k_group_pack<SG, false><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec, tflag, nullptr, nullptr);
     if (!launched("k_group_pack")) return -1;
     if (tiled) {
-        constexpr int G = SPNB_TILE_FWD_G;
+        constexpr int G = SPNB_TILE_FWD_G > 0 ? SPNB_TILE_FWD_G : (SG::fwd_vec() == 1 ? 1 : 2);
         const size_t smem = (size_t)SG::fwd_vec() * kTileCap * sizeof(float4);
         if (!allow_smem(k_tile_fwd<SG, G>, smem)) return -1;
         k_tile_fwd<SG, G><<<dim3(ta.ntb, B), kTileQ * G, smem, stream>>>(rec, ta, ga, N, K, BN);

@@ -406,7 +406,8 @@ __device__ __forceinline__ int key_lower_bound(const uint32_t* __restrict__ k, i
 }
 
 __global__ void __launch_bounds__(256)
-k_tile_ranges(const uint32_t* __restrict__ keys, const float* __restrict__ grid_dims, int N, int D,
+k_tile_ranges(const uint32_t* __restrict__ keys, const float* __restrict__ grid_dims,
+              const float* __restrict__ starts, const float* __restrict__ ends, int N, int D,
               int ncells, int ntb, TileDesc* __restrict__ descs, int* flag)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -432,8 +433,22 @@ k_tile_ranges(const uint32_t* __restrict__ keys, const float* __restrict__ grid_
         if (lo < 0) lo = 0;
         if (hi > used - 1) hi = used - 1;
         if (lo <= hi) {
-            s = key_lower_bound(k, N, lo);
-            e = key_lower_bound(k, N, hi + 1);
+            if (starts != nullptr && hi - lo < 64) {
+                // the cell table answers both bounds with one load each unless border cells are empty
+                // (empty cells read start == end == 0)
+                const float* st = starts + (size_t)b * ncells;
+                const float* en = ends + (size_t)b * ncells;
+                long long c0 = lo, c1 = hi;
+                while (c0 <= hi && !(en[c0] > st[c0])) ++c0;
+                while (c1 >= c0 && !(en[c1] > st[c1])) --c1;
+                if (c0 <= c1) {
+                    s = (int)st[c0];
+                    e = (int)en[c1];
+                }
+            } else {
+                s = key_lower_bound(k, N, lo);
+                e = key_lower_bound(k, N, hi + 1);
+            }
         }
     }
     int rs[kTileMaxRanges], re[kTileMaxRanges];
@@ -497,16 +512,14 @@ k_tile_ranges(const uint32_t* __restrict__ keys, const float* __restrict__ grid_
 constexpr int kQPW = 8;          // queries per warp
 constexpr int kCollideWarps = 8;  // warps per block
 
-template <int DT, bool TILES>
+template <int DT>
 __global__ void __launch_bounds__(kCollideWarps * 32)
 k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
           const float* __restrict__ low, const float* __restrict__ grid_dims,
           const float* __restrict__ starts, const float* __restrict__ ends,
           float* __restrict__ coll, int M, int N, int ndims, int K, int ncells, float edge, float r2,
-          int include_self, int* trunc_flag, const TileDesc* __restrict__ descs, int* __restrict__ tcounts,
-          unsigned short* __restrict__ tlists, int ntb, int* tile_flag)
+          int include_self, int* trunc_flag)
 {
-    static_assert(!TILES || kCollideWarps * kQPW == kTileQ, "a collide block is one tile block");
     constexpr int MD = DT > 0 ? DT : SPNB_MAXD;
     constexpr int CM = DT > 0 ? 256 : 64;  // staged candidates per window
     const int D = DT > 0 ? DT : ndims;
@@ -515,18 +528,9 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
     __shared__ int s_idx[kCollideWarps][CM];
     __shared__ float s_y[kCollideWarps][MD][CM];
     __shared__ int s_found[kCollideWarps][kQPW];
-    __shared__ unsigned short s_loc[kCollideWarps][TILES ? CM : 1];
-    __shared__ TileDesc s_desc;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
-    if (TILES) {
-        // the compact lists of this block's 64 queries index into the tile described by s_desc
-        if (threadIdx.x < (int)(sizeof(TileDesc) / sizeof(int)))
-            reinterpret_cast<int*>(&s_desc)[threadIdx.x] =
-                reinterpret_cast<const int*>(descs + (size_t)b * ntb + blockIdx.x)[threadIdx.x];
-        __syncthreads();
-    }
     const int q0 = (blockIdx.x * kCollideWarps + warp) * kQPW;
     if (q0 >= M) return;
     const int nq = min(kQPW, M - q0);
@@ -541,7 +545,6 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
 #pragma unroll
     for (int k = 0; k < D; ++k) total_cells *= 3;
     bool truncated = false;
-    bool tile_wide = false;
 
     int qi = 0;
     while (qi < nq) {
@@ -604,14 +607,6 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
                         if (s_off[warp][c + s] <= tt) c += s;
                     const int idx = s_start[warp][c] + (tt - s_off[warp][c]);
                     s_idx[warp][t] = idx;
-                    if (TILES) {
-                        int loc = 0;  // slot of particle idx in the staged tile (ranges ascend)
-#pragma unroll
-                        for (int r = 0; r < kTileMaxRanges; ++r)
-                            if (r < s_desc.nr && idx >= s_desc.start[r]) loc = 1 + s_desc.prefix[r] + idx - s_desc.start[r];
-                        if (loc > 0xffff) tile_wide = true;  // slot does not fit 16 bits: sidecar unusable
-                        s_loc[warp][t] = (unsigned short)loc;
-                    }
 #pragma unroll
                     for (int k = 0; k < D; ++k) s_y[warp][k][t] = sl[(size_t)idx * D + k];
                 }
@@ -624,8 +619,6 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
 #pragma unroll
                     for (int k = 0; k < D; ++k) x[k] = sq[(qi + r) * D + k];
                     float* row = rows + (size_t)(qi + r) * K;
-                    unsigned short* trow = nullptr;
-                    if (TILES) trow = tlists + tile_entry_off(ntb, K, b, blockIdx.x, warp * kQPW + qi + r, 0) / 2;
                     for (int base = 0; base < wn && found < K; base += 32) {
                         const int t = base + lane;
                         bool hit = false;
@@ -642,10 +635,7 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
                         }
                         const unsigned m = __ballot_sync(0xffffffffu, hit);
                         const int pos = found + __popc(m & lanemask_lt());
-                        if (hit && pos < K) {
-                            row[pos] = (float)idx;
-                            if (TILES) trow[(pos >> 4) * 128 + (pos & 15)] = s_loc[warp][t];
-                        }
+                        if (hit && pos < K) row[pos] = (float)idx;
                         found += __popc(m);
                     }
                     if (lane == 0) s_found[warp][r] = found;
@@ -662,20 +652,77 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
             }
             float* row = rows + (size_t)(qi + r) * K;
             for (int p = found + lane; p < K; p += 32) row[p] = -1.0f;
-            if (TILES) {
-                // sentinel-fill the tail of the last unit, publish the length
-                unsigned short* trow = tlists + tile_entry_off(ntb, K, b, blockIdx.x, warp * kQPW + qi + r, 0) / 2;
-                const int p = found + lane;
-                if (p < ((found + kTileUnit - 1) & ~(kTileUnit - 1))) trow[(p >> 4) * 128 + (p & 15)] = 0;
-                if (lane == 0) tcounts[(size_t)b * N + q0 + qi + r] = found;
-            }
         }
         __syncwarp();
         qi += run;
     }
     if (truncated && trunc_flag && lane == 0) atomicOr(trunc_flag, 1);
-    if (TILES && truncated && lane == 0) atomicOr(tile_flag, 1);
-    if (TILES && tile_wide) atomicOr(tile_flag, 2);
+}
+
+// ---- tile lists (tile_lists.cuh) ---------------------------------------------------------------------
+// One block per tile block of 64 queries, run after k_collide on the float rows it wrote: every warp
+// reads the rows of 8 queries (coalesced 128-byte chunks up to the terminator), maps each neighbour
+// index to its slot in the block's candidate ranges (TileDesc: ascending range starts kept in
+// registers) and writes the 16-bit entry, the sentinel padding of the last unit and the list length.
+constexpr int kBuildThreads = 256;
+
+__global__ void __launch_bounds__(kBuildThreads)
+k_tile_build(const float* __restrict__ coll, const TileDesc* __restrict__ descs, int N, int K, int ntb,
+             int* __restrict__ tile_flag, int* __restrict__ tcounts, unsigned short* __restrict__ tlists)
+{
+    __shared__ TileDesc s_desc;
+    __shared__ int s_fwd[kTileMaxRanges], s_len[kTileMaxRanges];  // idx -> slot: idx + s_fwd[r]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tb = blockIdx.x, b = blockIdx.y;
+    const size_t tile = (size_t)b * ntb + tb;
+    if (tid < (int)(sizeof(TileDesc) / sizeof(int)))
+        reinterpret_cast<int*>(&s_desc)[tid] = reinterpret_cast<const int*>(descs + tile)[tid];
+    __syncthreads();
+    int st[kTileMaxRanges];
+#pragma unroll
+    for (int g = 0; g < kTileMaxRanges; ++g) st[g] = g < s_desc.nr ? s_desc.start[g] : 0x7fffffff;
+    if (tid < kTileMaxRanges) {
+        s_fwd[tid] = 1 + s_desc.prefix[tid] - s_desc.start[tid];
+        s_len[tid] = tid < s_desc.nr ? s_desc.prefix[tid + 1] - s_desc.prefix[tid] : 0;
+    }
+    __syncthreads();
+
+    bool bad = false, cut = false;
+    constexpr int RPW = kTileQ / (kBuildThreads / 32);  // rows per warp
+    for (int r = 0; r < RPW; ++r) {
+        const int ql = warp * RPW + r;
+        const int m = tb * kTileQ + ql;
+        if (m >= N) break;
+        const float* row = coll + ((size_t)b * N + m) * K;
+        unsigned short* trow = tlists + tile_entry_off(ntb, K, b, tb, ql, 0) / 2;
+        int cnt = 0;
+        for (int base = 0; base < K; base += 32) {
+            const int k = base + lane;
+            const float f = k < K ? row[k] : -1.0f;
+            const unsigned neg = __ballot_sync(0xffffffffu, !(f >= 0.0f));
+            const int take = neg ? __ffs(neg) - 1 : 32;  // entries before the terminator
+            unsigned loc = 0;                            // lanes past it write the sentinel padding
+            if (lane < take) {
+                const int idx = (int)f;
+                int g = 0;
+#pragma unroll
+                for (int t = 1; t < kTileMaxRanges; ++t) g += idx >= st[t];
+                loc = (unsigned)(idx + s_fwd[g]);
+                if ((unsigned)(idx - st[g]) >= (unsigned)s_len[g] || loc > 0xffffu) {
+                    bad = true;  // not in the block's ranges, or the slot does not fit 16 bits
+                    loc = 0;
+                }
+            }
+            if (lane < ((take + kTileUnit - 1) & ~(kTileUnit - 1)) && k < K)
+                trow[(k >> 4) * 128 + (k & 15)] = (unsigned short)loc;
+            cnt += take;
+            if (take < 32) break;
+        }
+        if (cnt >= K) cut = true;
+        if (lane == 0) tcounts[(size_t)b * N + m] = cnt;
+    }
+    if (cut && lane == 0) atomicOr(tile_flag, 1);
+    if (bad) atomicOr(tile_flag, 2);
 }
 
 // ---- launch helpers --------------------------------------------------------------------------------
@@ -833,17 +880,11 @@ int spnb_reorder_data(const float* locs, const float* data, const float* idxs, f
     return check_launch("spnb_reorder_data") ? 1 : 0;
 }
 
-size_t spnb_tile_lists_bytes(int batch_size, int N, int ndims, int max_collisions)
-{
-    if (batch_size <= 0 || !tile_lists_supported(N, ndims, max_collisions)) return 0;
-    return tile_layout(batch_size, N, max_collisions).total;
-}
-
-static int collide_impl(const float* qlocs, const float* locs, const float* low,
-                        const float* grid_dims, const float* cellIDs, float* cellStarts,
-                        float* cellEnds, float* collisions, int B, int M, int N, int D, int K,
-                        int ncells, float cellEdge, float radius, int include_self,
-                        int* trunc_flag, void* tiles, size_t tiles_bytes, void* stream_)
+int spnb_compute_collisions(const float* qlocs, const float* locs, const float* low,
+                            const float* grid_dims, const float* cellIDs, float* cellStarts,
+                            float* cellEnds, float* collisions, int B, int M, int N, int D, int K,
+                            int ncells, float cellEdge, float radius, int include_self,
+                            int* trunc_flag, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!valid_common(B, N, D, "spnb_compute_collisions")) return 0;
@@ -860,42 +901,10 @@ static int collide_impl(const float* qlocs, const float* locs, const float* low,
                                                             cellStarts, cellEnds, N, D, ncells);
     const float r2 = radius * radius;
     const dim3 blocks(cdiv(M, kCollideWarps * kQPW), B);
-    if (tiles) {
-        if (qlocs != locs || M != N || !tile_lists_supported(N, D, K)) {
-            set_error("spnb_compute_collisions_tiled: needs qlocs == locs and ndims <= %d, max_collisions %% %d == 0",
-                      kTileMaxNdim, kTileUnit);
-            return 0;
-        }
-        const TileLayout tl = tile_layout(B, N, K);
-        if (tiles_bytes < tl.total) {
-            set_error("spnb_compute_collisions_tiled: tile buffer too small (%zu < %zu)", tiles_bytes, tl.total);
-            return 0;
-        }
-        char* tb = (char*)tiles;
-        int* tflag = (int*)tb;
-        TileDesc* descs = (TileDesc*)(tb + tl.desc_off);
-        int* tcounts = (int*)(tb + tl.cnt_off);
-        unsigned short* tlists = (unsigned short*)(tb + tl.list_off);
-        cudaMemsetAsync(tflag, 0, 128, stream);
-        k_tile_ranges<<<dim3(cdiv(tl.ntb, 8), B), 256, 0, stream>>>((const uint32_t*)cellIDs, grid_dims, N, D,
-                                                                    ncells, tl.ntb, descs, tflag);
-#define SPNB_COLLIDE_T(DT)                                                                        \
-    k_collide<DT, true><<<blocks, kCollideWarps * 32, 0, stream>>>(                                \
-        qlocs, locs, low, grid_dims, cellStarts, cellEnds, collisions, M, N, D, K, ncells, cellEdge, \
-        r2, include_self, trunc_flag, descs, tcounts, tlists, tl.ntb, tflag)
-        switch (D) {
-        case 1: SPNB_COLLIDE_T(1); break;
-        case 2: SPNB_COLLIDE_T(2); break;
-        default: SPNB_COLLIDE_T(3); break;
-        }
-#undef SPNB_COLLIDE_T
-        count_launches(4);
-        return check_launch("spnb_compute_collisions_tiled") ? 1 : 0;
-    }
 #define SPNB_COLLIDE(DT)                                                                          \
-    k_collide<DT, false><<<blocks, kCollideWarps * 32, 0, stream>>>(                               \
+    k_collide<DT><<<blocks, kCollideWarps * 32, 0, stream>>>(                                      \
         qlocs, locs, low, grid_dims, cellStarts, cellEnds, collisions, M, N, D, K, ncells, cellEdge, \
-        r2, include_self, trunc_flag, nullptr, nullptr, nullptr, 0, nullptr)
+        r2, include_self, trunc_flag)
     switch (D) {
     case 1: SPNB_COLLIDE(1); break;
     case 2: SPNB_COLLIDE(2); break;
@@ -907,28 +916,43 @@ static int collide_impl(const float* qlocs, const float* locs, const float* low,
     return check_launch("spnb_compute_collisions") ? 1 : 0;
 }
 
-int spnb_compute_collisions(const float* qlocs, const float* locs, const float* low,
-                            const float* grid_dims, const float* cellIDs, float* cellStarts,
-                            float* cellEnds, float* collisions, int B, int M, int N, int D, int K,
-                            int ncells, float cellEdge, float radius, int include_self,
-                            int* trunc_flag, void* stream_)
+size_t spnb_tile_lists_bytes(int batch_size, int N, int ndims, int max_collisions)
 {
-    return collide_impl(qlocs, locs, low, grid_dims, cellIDs, cellStarts, cellEnds, collisions, B, M, N, D, K,
-                        ncells, cellEdge, radius, include_self, trunc_flag, nullptr, 0, stream_);
+    if (batch_size <= 0 || !tile_lists_supported(N, ndims, max_collisions)) return 0;
+    return tile_layout(batch_size, N, max_collisions).total;
 }
 
-int spnb_compute_collisions_tiled(const float* qlocs, const float* locs, const float* low,
-                                  const float* grid_dims, const float* cellIDs, float* cellStarts,
-                                  float* cellEnds, float* collisions, int B, int M, int N, int D, int K,
-                                  int ncells, float cellEdge, float radius, int include_self,
-                                  int* trunc_flag, void* tile_lists, size_t tile_lists_bytes, void* stream_)
+int spnb_build_tile_lists(const float* cellIDs, const float* grid_dims, const float* cellStarts,
+                          const float* cellEnds, const float* collisions, int B, int N, int D, int K,
+                          int ncells, void* tile_lists, size_t tile_lists_bytes, void* stream_)
 {
-    if (!tile_lists) {
-        set_error("spnb_compute_collisions_tiled: null tile buffer");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!valid_common(B, N, D, "spnb_build_tile_lists")) return 0;
+    if (!cellIDs || !grid_dims || !collisions || !tile_lists) {
+        set_error("spnb_build_tile_lists: null pointer");
         return 0;
     }
-    return collide_impl(qlocs, locs, low, grid_dims, cellIDs, cellStarts, cellEnds, collisions, B, M, N, D, K,
-                        ncells, cellEdge, radius, include_self, trunc_flag, tile_lists, tile_lists_bytes, stream_);
+    if (!tile_lists_supported(N, D, K)) {
+        set_error("spnb_build_tile_lists: needs ndims <= %d and max_collisions a multiple of %d",
+                  kTileMaxNdim, kTileUnit);
+        return 0;
+    }
+    const TileLayout tl = tile_layout(B, N, K);
+    if (tile_lists_bytes < tl.total) {
+        set_error("spnb_build_tile_lists: tile buffer too small (%zu < %zu)", tile_lists_bytes, tl.total);
+        return 0;
+    }
+    char* tb = (char*)tile_lists;
+    int* tflag = (int*)tb;
+    TileDesc* descs = (TileDesc*)(tb + tl.desc_off);
+    cudaMemsetAsync(tflag, 0, 128, stream);
+    k_tile_ranges<<<dim3(cdiv(tl.ntb, 8), B), 256, 0, stream>>>((const uint32_t*)cellIDs, grid_dims,
+                                                                cellEnds ? cellStarts : nullptr, cellEnds, N, D,
+                                                                ncells, tl.ntb, descs, tflag);
+    k_tile_build<<<dim3(tl.ntb, B), kBuildThreads, 0, stream>>>(
+        collisions, descs, N, K, tl.ntb, tflag, (int*)(tb + tl.cnt_off), (unsigned short*)(tb + tl.list_off));
+    count_launches(2);
+    return check_launch("spnb_build_tile_lists") ? 1 : 0;
 }
 
 }  // extern "C"

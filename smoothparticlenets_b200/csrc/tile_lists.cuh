@@ -2,7 +2,8 @@
 //
 // The API-visible neighbour tensor stays [B,M,K] float32, -1 terminated (ParticleCollision.py:129-135).
 // Next to it ParticleCollision can emit the SAME lists (same entries, same order, same truncation)
-// in a form the ConvSP kernels can consume at close to HBM speed:
+// in a form the ConvSP kernels can consume faster (spnb_build_tile_lists: k_tile_ranges + k_tile_build
+// in hashgrid.cu, run on the float rows k_collide wrote):
 //
 //  * the cell-sorted particles of a scene are cut into TILE BLOCKS of kTileQ = 64 consecutive
 //    queries.  Because the cell hash is row-major (common_funcs.h:114-118), every neighbour of such
@@ -22,9 +23,14 @@
 // A tile with more than kTileCap - 1 records is not staged: its block resolves slots back to sorted
 // indices through the TileDesc and gathers from global memory (rare: dense clumps).
 //
-// flag (first int of the buffer) != 0 marks the sidecar unusable for this call: bit 0 = a list was cut
-// at K (the symmetric backward is then invalid, see convsp_group.cu), bit 1 = a tile has more than
-// 65535 records.  Consumers test it on the DEVICE and the ordinary list walk runs instead, so nothing
+// Measured alternative (profiles/README.md): staging only the ~400 records a block's lists actually
+// reference (an index list per tile, cp.async gathers, lists renumbered and sorted) halves the staged
+// bytes but gave the same kernel times -- the consumers are bound by the shared-memory pipe (random
+// LDS.128 gathers conflict ~2x), not by staging -- while its builder cost 4x more; not kept.
+//
+// flag (first int of the buffer) != 0 marks the sidecar unusable for this call: bit 0 = a list is full,
+// i.e. may have been cut at K (the symmetric backward is then invalid, see convsp_group.cu), bit 1 = a
+// neighbour lies outside the block's ranges or a tile has more than 65535 records.  Consumers test it on the DEVICE and the ordinary list walk runs instead, so nothing
 // depends on a host synchronisation.
 #pragma once
 #include <stddef.h>

@@ -186,26 +186,23 @@ class ParticleCollision(torch.nn.Module):
             neighbors = torch.empty(batch_size, M, self.max_collisions, device=dev,
                                     dtype=torch.float32)
             trunc = torch.zeros(1, device=dev, dtype=torch.int32)
+            nat.check(L.spnb_compute_collisions(
+                nat.ptr(q), nat.ptr(locs.detach()), nat.ptr(lower_bounds), nat.ptr(grid_dims),
+                nat.ptr(cellIDs), nat.ptr(cellStarts), nat.ptr(cellEnds), nat.ptr(neighbors),
+                batch_size, M, N, D, self.max_collisions, ncells, float(self.radius),
+                float(self.radius), self.include_self, nat.ptr(trunc), nat.stream()),
+                "spnb_compute_collisions")
             tiles = None
             tile_bytes = (L.spnb_tile_lists_bytes(batch_size, N, D, self.max_collisions)
                           if qlocs is None and self.tile_lists else 0)
             if tile_bytes > 0:
                 # compact sidecar of the same lists (csrc/tile_lists.cuh) for the ConvSPGroup kernels
                 tiles = torch.empty(tile_bytes, device=dev, dtype=torch.uint8)
-                ls = locs.detach()
-                nat.check(L.spnb_compute_collisions_tiled(
-                    nat.ptr(ls), nat.ptr(ls), nat.ptr(lower_bounds), nat.ptr(grid_dims),
-                    nat.ptr(cellIDs), nat.ptr(cellStarts), nat.ptr(cellEnds), nat.ptr(neighbors),
-                    batch_size, M, N, D, self.max_collisions, ncells, float(self.radius),
-                    float(self.radius), self.include_self, nat.ptr(trunc), nat.ptr(tiles), tile_bytes,
-                    nat.stream()), "spnb_compute_collisions_tiled")
-            else:
-                nat.check(L.spnb_compute_collisions(
-                    nat.ptr(q), nat.ptr(locs.detach()), nat.ptr(lower_bounds), nat.ptr(grid_dims),
-                    nat.ptr(cellIDs), nat.ptr(cellStarts), nat.ptr(cellEnds), nat.ptr(neighbors),
-                    batch_size, M, N, D, self.max_collisions, ncells, float(self.radius),
-                    float(self.radius), self.include_self, nat.ptr(trunc), nat.stream()),
-                    "spnb_compute_collisions")
+                nat.check(L.spnb_build_tile_lists(
+                    nat.ptr(cellIDs), nat.ptr(grid_dims), nat.ptr(cellStarts), nat.ptr(cellEnds),
+                    nat.ptr(neighbors), batch_size, N, D,
+                    self.max_collisions, ncells, nat.ptr(tiles), tile_bytes, nat.stream()),
+                    "spnb_build_tile_lists")
         if qlocs is None:
             # Lists built with the particles as their own queries are symmetric unless one was cut
             # at max_collisions; ConvSP's backward uses this to avoid atomics.

@@ -229,13 +229,14 @@ def test_tile_lists_full_size(spn):
     assert (totals + 1 > tl.TILE_CAP).mean() < 0.01, "tiles that do not fit the staging capacity are rare"
     counts = raw[lay["cnt_off"]:lay["cnt_off"] + 4 * B * N].view(np.int32).reshape(B, N)
     assert np.array_equal(counts, gu.host((nb >= 0).sum(2)))
-    # decode scene 5 only (python loop): slice a one-scene view of the buffer
-    b = 5
-    one = np.concatenate([
-        raw[:128], desc[b].reshape(-1).view(np.uint8),
-        np.zeros(tl.layout(1, N, K)["list_off"] - tl.layout(1, N, K)["cnt_off"], np.uint8),
-        raw[lay["list_off"] + b * lay["ntb"] * tl.TILE_Q * K * 2: lay["list_off"] + (b + 1) * lay["ntb"] * tl.TILE_Q * K * 2]])
-    l1 = tl.layout(1, N, K)
-    one[l1["cnt_off"]:l1["cnt_off"] + 4 * N] = counts[b].view(np.uint8)
-    flag, c1, dec, _ = tl.decode(one, 1, N, K)
-    assert np.array_equal(dec[0], gu.host(nb[b]).astype(np.int64))
+    # decode the first 24 tile blocks of scene 5 (python loop): assemble a small one-scene buffer
+    b, nt = 5, 24
+    Ns = nt * tl.TILE_Q
+    l1 = tl.layout(1, Ns, K)
+    one = np.zeros(l1["total"], np.uint8)
+    one[l1["desc_off"]:l1["cnt_off"]] = desc[b, :nt].copy().reshape(-1).view(np.uint8)
+    one[l1["cnt_off"]:l1["cnt_off"] + 4 * Ns] = counts[b, :Ns].copy().view(np.uint8)
+    s0 = lay["list_off"] + b * lay["ntb"] * tl.TILE_Q * K * 2
+    one[l1["list_off"]:] = raw[s0:s0 + nt * tl.TILE_Q * K * 2]
+    flag, c1, dec, _ = tl.decode(one, 1, Ns, K)
+    assert np.array_equal(dec[0], gu.host(nb[b, :Ns]).astype(np.int64))
