@@ -89,6 +89,8 @@ class FluidStep(nn.Module):
             setattr(self, "%s%s%s" % (kernel, "D" if dim == 'D' else "1", "normd" if normed else ""), conv)
         self.register_buffer("gravity", torch.tensor(GRAVITY[:ndim], dtype=torch.float32).view(1, 1, -1))
         self.relu = nn.ReLU()
+        # fused=True also uses the namespace's fused elementwise solver stages when it has them (pbf.py)
+        self.pbf = ns if (self.fused and hasattr(ns, "pbf_stage1")) else None
         if self.fused:
             self.group_a = ns.ConvSPGroup([self.spiky1, self.dspikyDnormd, self.dspiky1normd,
                                            self.cohesionDnormd, self.cohesion1normd, self.constant1])
@@ -109,7 +111,19 @@ class FluidStep(nn.Module):
         vel = self._cap_magnitude(vel, self.max_speed)
         new_locs = locs + vel * dt
         new_locs, vel, pidxs, neighbors = self.coll(new_locs, vel)
-        for _ in range(NUM_ITERATIONS if self.fused else 0):
+        for _ in range(NUM_ITERATIONS if self.pbf is not None else 0):
+            # same data flow as below; the elementwise arithmetic between the groups in three fused stages
+            pbf = self.pbf
+            density, nj, ni_s, nj_c, ni_cs, ncount = self.group_a(
+                new_locs, [ones, new_locs, ones, new_locs, ones, ones], neighbors)
+            pressure, xp, nij = pbf.pbf_stage1(new_locs, density, nj, ni_s, self.stiffness, self.density_rest)
+            njp, nip_s = self.group_b(new_locs, [xp, pressure], neighbors)
+            delta0, normals = pbf.pbf_stage2(new_locs, pressure, nij, njp, nip_s, nj_c, ni_cs, COHESION,
+                                             self.radius, SURFACE_TENSION, self.density_rest,
+                                             SURFACE_CONSTRAINT_SCALE)
+            cd, = self.group_c(new_locs, [normals], neighbors)
+            new_locs = pbf.pbf_stage3(new_locs, delta0, cd, normals, ncount, RELAXATION, DAMP)
+        for _ in range(NUM_ITERATIONS if (self.fused and self.pbf is None) else 0):
             # same data flow as below; layers sharing (new_locs, neighbors) grouped by dependency
             density, nj, ni_s, nj_c, ni_cs, ncount = self.group_a(
                 new_locs, [ones, new_locs, ones, new_locs, ones, ones], neighbors)

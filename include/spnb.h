@@ -172,6 +172,33 @@ int spnb_convsp_group_backward(const float* locs, const float* neighbors, int ba
                                float* dlocs, const int* sym_flag, void* workspace, size_t workspace_bytes,
                                const void* tile_lists, void* stream);
 
+/* ---- fused elementwise stages of the PBF solver iteration (no reference counterpart; 8(f) rank 1) -- */
+
+/* The per-particle arithmetic examples/fluid_sim.py:367-397 performs with torch ops between the ConvSP
+ * layers of one solver iteration, one launch per stage (csrc/fluid_glue.cu has the formulas).  Vectors
+ * are [BN, ndims], scalars [BN]; gradient INPUTS may be NULL (= zero). */
+int spnb_pbf_stage1_forward(const float* x, const float* density, const float* nj, const float* ni_s, float* p,
+                            float* xp, float* nij, long long BN, int ndims, float stiffness, float rho0,
+                            void* stream);
+int spnb_pbf_stage1_backward(const float* x, const float* density, const float* ni_s, const float* g_p,
+                             const float* g_xp, const float* g_nij, float* g_x, float* g_density, float* g_nj,
+                             float* g_ni_s, long long BN, int ndims, float stiffness, float rho0, void* stream);
+int spnb_pbf_stage2_forward(const float* x, const float* p, const float* nij, const float* njp,
+                            const float* nip_s, const float* nj_c, const float* ni_cs, float* d0, float* nrm,
+                            long long BN, int ndims, float cohesion, float radius, float surface_tension,
+                            float rho0, float constraint_scale, void* stream);
+int spnb_pbf_stage2_backward(const float* x, const float* p, const float* nij, const float* nip_s,
+                             const float* ni_cs, const float* g_d0, const float* g_nrm, float* g_x, float* g_p,
+                             float* g_nij, float* g_njp, float* g_nip_s, float* g_nj_c, float* g_ni_cs,
+                             long long BN, int ndims, float cohesion, float radius, float surface_tension,
+                             float rho0, float constraint_scale, void* stream);
+int spnb_pbf_stage3_forward(const float* x, const float* d0, const float* cd, const float* nrm,
+                            const float* ncount, float* xnew, long long BN, int ndims, float relaxation,
+                            float damp, void* stream);
+int spnb_pbf_stage3_backward(const float* d0, const float* cd, const float* nrm, const float* ncount,
+                             const float* g, float* g_d0, float* g_nrm, float* g_ncount, long long BN,
+                             int ndims, float relaxation, float damp, void* stream);
+
 /* ---- ConvSDF ---------------------------------------------------------------------------------- */
 
 /* Forward (bias added in the kernel, as common_funcs.h:834-835).  Replaces cuda_convsdf with NULL

@@ -34,6 +34,12 @@ _SIGNATURES = {
     "spnb_convsp_group_workspace_bytes": (_sz, [_vp, _i, _i, _i, _f, _i, _vp, _i]),
     "spnb_convsp_group_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _sz, _vp, _vp]),
     "spnb_convsp_group_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "spnb_pbf_stage1_forward": (_i, [_vp] * 7 + [ctypes.c_longlong, _i, _f, _f, _vp]),
+    "spnb_pbf_stage1_backward": (_i, [_vp] * 10 + [ctypes.c_longlong, _i, _f, _f, _vp]),
+    "spnb_pbf_stage2_forward": (_i, [_vp] * 9 + [ctypes.c_longlong, _i, _f, _f, _f, _f, _f, _vp]),
+    "spnb_pbf_stage2_backward": (_i, [_vp] * 14 + [ctypes.c_longlong, _i, _f, _f, _f, _f, _f, _vp]),
+    "spnb_pbf_stage3_forward": (_i, [_vp] * 6 + [ctypes.c_longlong, _i, _f, _f, _vp]),
+    "spnb_pbf_stage3_backward": (_i, [_vp] * 8 + [ctypes.c_longlong, _i, _f, _f, _vp]),
     "spnb_convsdf_forward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp, _i, _vp,
                                   _vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "spnb_convsdf_backward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp, _i, _vp,

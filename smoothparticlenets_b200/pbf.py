@@ -1,0 +1,130 @@
+"""Fused per-particle stages of the Position-Based-Fluids solver iteration (csrc/fluid_glue.cu).
+
+An opt-in extension like ConvSPGroup, not part of the reference API: the
+elementwise arithmetic that examples/fluid_sim.py:367-397 writes as ~35 tiny torch ops between the
+ConvSP layers of one solver iteration, as three differentiable ops with hand-derived backward
+kernels.  ``pbf_stage1/2/3`` return exactly what the torch expressions in their docstrings return
+(same operation order per element).  CUDA float32 tensors only; no fallback.
+"""
+import torch
+
+from . import _native as nat
+
+
+def _c(t):
+    return nat.require_cuda_f32(t.contiguous(), "pbf operand")
+
+
+def _z(g, like):
+    """Gradient or None -> contiguous tensor or None (the kernels treat NULL as zero)."""
+    return None if g is None else g.contiguous()
+
+
+class _Stage1(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, density, nj, ni_s, stiffness, rho0):
+        x, density, nj, ni_s = _c(x), _c(density), _c(nj), _c(ni_s)
+        BN, D = x.numel() // x.shape[-1], x.shape[-1]
+        p, xp, nij = torch.empty_like(density), torch.empty_like(x), torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            nat.check(nat.lib().spnb_pbf_stage1_forward(nat.ptr(x), nat.ptr(density), nat.ptr(nj), nat.ptr(ni_s),
+                                                        nat.ptr(p), nat.ptr(xp), nat.ptr(nij), BN, D,
+                                                        stiffness, rho0, nat.stream()), "spnb_pbf_stage1_forward")
+        ctx.save_for_backward(x, density, ni_s)
+        ctx.consts = (stiffness, rho0)
+        return p, xp, nij
+
+    @staticmethod
+    def backward(ctx, g_p, g_xp, g_nij):
+        x, density, ni_s = ctx.saved_tensors
+        BN, D = x.numel() // x.shape[-1], x.shape[-1]
+        g_p, g_xp, g_nij = _z(g_p, density), _z(g_xp, x), _z(g_nij, x)
+        g_x, g_nj = torch.empty_like(x), torch.empty_like(x)
+        g_density, g_ni_s = torch.empty_like(density), torch.empty_like(density)
+        with torch.cuda.device(x.device):
+            nat.check(nat.lib().spnb_pbf_stage1_backward(
+                nat.ptr(x), nat.ptr(density), nat.ptr(ni_s), nat.ptr(g_p), nat.ptr(g_xp), nat.ptr(g_nij),
+                nat.ptr(g_x), nat.ptr(g_density), nat.ptr(g_nj), nat.ptr(g_ni_s), BN, D, ctx.consts[0],
+                ctx.consts[1], nat.stream()), "spnb_pbf_stage1_backward")
+        return g_x, g_density, g_nj, g_ni_s, None, None
+
+
+class _Stage2(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, p, nij, njp, nip_s, nj_c, ni_cs, cohesion, radius, surface_tension, rho0, cscale):
+        x, p, nij, njp, nip_s, nj_c, ni_cs = [_c(t) for t in (x, p, nij, njp, nip_s, nj_c, ni_cs)]
+        BN, D = x.numel() // x.shape[-1], x.shape[-1]
+        d0, nrm = torch.empty_like(x), torch.empty_like(x)
+        consts = (cohesion, radius, surface_tension, rho0, cscale)
+        with torch.cuda.device(x.device):
+            nat.check(nat.lib().spnb_pbf_stage2_forward(
+                nat.ptr(x), nat.ptr(p), nat.ptr(nij), nat.ptr(njp), nat.ptr(nip_s), nat.ptr(nj_c), nat.ptr(ni_cs),
+                nat.ptr(d0), nat.ptr(nrm), BN, D, *consts, nat.stream()), "spnb_pbf_stage2_forward")
+        ctx.save_for_backward(x, p, nij, nip_s, ni_cs)
+        ctx.consts = consts
+        return d0, nrm
+
+    @staticmethod
+    def backward(ctx, g_d0, g_nrm):
+        x, p, nij, nip_s, ni_cs = ctx.saved_tensors
+        BN, D = x.numel() // x.shape[-1], x.shape[-1]
+        g_d0, g_nrm = _z(g_d0, x), _z(g_nrm, x)
+        g_x, g_nij, g_njp, g_nj_c = (torch.empty_like(x) for _ in range(4))
+        g_p, g_nip_s, g_ni_cs = (torch.empty_like(p) for _ in range(3))
+        with torch.cuda.device(x.device):
+            nat.check(nat.lib().spnb_pbf_stage2_backward(
+                nat.ptr(x), nat.ptr(p), nat.ptr(nij), nat.ptr(nip_s), nat.ptr(ni_cs), nat.ptr(g_d0), nat.ptr(g_nrm),
+                nat.ptr(g_x), nat.ptr(g_p), nat.ptr(g_nij), nat.ptr(g_njp), nat.ptr(g_nip_s), nat.ptr(g_nj_c),
+                nat.ptr(g_ni_cs), BN, D, *ctx.consts, nat.stream()), "spnb_pbf_stage2_backward")
+        return g_x, g_p, g_nij, g_njp, g_nip_s, g_nj_c, g_ni_cs, None, None, None, None, None
+
+
+class _Stage3(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, d0, cd, nrm, ncount, relaxation, damp):
+        x, d0, cd, nrm, ncount = [_c(t) for t in (x, d0, cd, nrm, ncount)]
+        BN, D = x.numel() // x.shape[-1], x.shape[-1]
+        xnew = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            nat.check(nat.lib().spnb_pbf_stage3_forward(
+                nat.ptr(x), nat.ptr(d0), nat.ptr(cd), nat.ptr(nrm), nat.ptr(ncount), nat.ptr(xnew), BN, D,
+                relaxation, damp, nat.stream()), "spnb_pbf_stage3_forward")
+        ctx.save_for_backward(d0, cd, nrm, ncount)
+        ctx.consts = (relaxation, damp)
+        return xnew
+
+    @staticmethod
+    def backward(ctx, g):
+        d0, cd, nrm, ncount = ctx.saved_tensors
+        BN, D = d0.numel() // d0.shape[-1], d0.shape[-1]
+        g = g.contiguous()
+        g_d0, g_nrm, g_ncount = torch.empty_like(d0), torch.empty_like(d0), torch.empty_like(ncount)
+        with torch.cuda.device(d0.device):
+            nat.check(nat.lib().spnb_pbf_stage3_backward(
+                nat.ptr(d0), nat.ptr(cd), nat.ptr(nrm), nat.ptr(ncount), nat.ptr(g), nat.ptr(g_d0), nat.ptr(g_nrm),
+                nat.ptr(g_ncount), BN, D, ctx.consts[0], ctx.consts[1], nat.stream()), "spnb_pbf_stage3_backward")
+        # d(xnew)/dx = 1 and d/d(cd) = d/d(d0)
+        return g, g_d0, g_d0, g_nrm, g_ncount, None, None
+
+
+def pbf_stage1(x, density, nj, ni_s, stiffness, rest_density):
+    """p = stiffness * relu(density - rest_density);  returns (p, x * p, x * ni_s - nj)."""
+    return _Stage1.apply(x, density, nj, ni_s, float(stiffness), float(rest_density))
+
+
+def pbf_stage2(x, p, nij, njp, nip_s, nj_c, ni_cs, cohesion, radius, surface_tension, rest_density,
+               constraint_scale):
+    """nijp = x * nip_s - njp;  nij2 = x * ni_cs - nj_c;
+    returns (-(p * nij + nijp) + -cohesion * nij2 * radius,
+             nij2 * surface_tension / rest_density / constraint_scale)."""
+    return _Stage2.apply(x, p, nij, njp, nip_s, nj_c, ni_cs, float(cohesion), float(radius),
+                         float(surface_tension), float(rest_density), float(constraint_scale))
+
+
+def pbf_stage3(x, d0, cd, normals, ncount, relaxation, damp):
+    """delta = d0 + (cd - normals * ncount);  scale = relu(ncount / (1 + relaxation) - damp) + damp;
+    returns x + delta / scale."""
+    return _Stage3.apply(x, d0, cd, normals, ncount, float(relaxation), float(damp))

@@ -164,3 +164,50 @@ def test_group_oversized_tiles_gather_from_global(spn):
     for i, (a, b) in enumerate(zip(res[True][0], res[False][0])):
         close(a, b, "layer %d forward" % i)
     close(res[True][1], res[False][1], "locs.grad", k=16)
+
+
+def test_pbf_stages_match_torch_expressions(spn):
+    """The fused elementwise solver stages (csrc/fluid_glue.cu) against the torch expressions of
+    examples/fluid_sim.py:367-397 they replace: forward values and every input gradient."""
+    B, N, D = 2, 1000, 3
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rnd = lambda *s: torch.rand(*s, device="cuda", generator=g)
+    k, rho0, coh, rad, st, cs, relax, damp = 0.37, 0.45, 0.1, 0.1, 0.3, 7.0, 1.0, 1.0
+
+    def run(fused):
+        x, nj, njp, nj_c, cd = (rnd(B, N, D).requires_grad_(True) for _ in range(5))
+        density, ni_s, nip_s, ni_cs = (rnd(B, N, 1).requires_grad_(True) for _ in range(4))
+        ncount = (rnd(B, N, 1) * 6).requires_grad_(True)
+        ins = [x, nj, njp, nj_c, cd, density, ni_s, nip_s, ni_cs, ncount]
+        if fused:
+            p, xp, nij = spn.pbf_stage1(x, density, nj, ni_s, k, rho0)
+            d0, nrm = spn.pbf_stage2(x, p, nij, njp, nip_s, nj_c, ni_cs, coh, rad, st, rho0, cs)
+            xn = spn.pbf_stage3(x, d0, cd, nrm, ncount, relax, damp)
+        else:
+            relu = torch.nn.functional.relu
+            p = k * relu(density - rho0)
+            xp = x * p
+            nij = x * ni_s - nj
+            nijp = x * nip_s - njp
+            d0 = -(p * nij + nijp)
+            nij2 = x * ni_cs - nj_c
+            d0 = d0 + -coh * nij2 * rad
+            nrm = nij2 * st / rho0 / cs
+            delta = d0 + (cd - nrm * ncount)
+            scale = relu(ncount / (1.0 + relax) - damp) + damp
+            xn = x + delta / scale
+        outs = [p, xp, nij, d0, nrm, xn]
+        return ins, outs
+
+    res = {}
+    for fused in (True, False):
+        g.manual_seed(5)
+        ins, outs = run(fused)
+        gg = torch.Generator(device="cuda").manual_seed(9)
+        gos = [torch.rand(o.shape, device="cuda", generator=gg) for o in outs]
+        torch.autograd.backward(outs, gos)
+        res[fused] = ([o.detach() for o in outs], [i.grad for i in ins])
+    for i, (a, b) in enumerate(zip(res[True][0], res[False][0])):
+        close(a, b, "pbf output %d" % i)
+    for i, (a, b) in enumerate(zip(res[True][1], res[False][1])):
+        close(a, b, "pbf input gradient %d" % i, k=16)
