@@ -227,10 +227,29 @@ k_group_pack(const float* __restrict__ locs, GroupArgs ga, long long BN, float* 
     for (int v = 0; v < V; ++v) dst[v * vs] = make_float4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
 }
 
+// Per-layer kernel coefficients copied out of the parameter block once per thread (the tile kernels keep
+// them in registers: re-reading the constant bank per pair costs ~3 issue slots per pair).
+template <int NL>
+struct LayerCoef {
+    struct { float wc, dwc; } l[NL];
+};
+template <typename SG>
+__device__ __forceinline__ LayerCoef<SG::NL> load_coef(const GroupArgs& ga)
+{
+    LayerCoef<SG::NL> c;
+#pragma unroll
+    for (int l = 0; l < SG::NL; ++l) {
+        c.l[l].wc = ga.l[l].wc;
+        c.l[l].dwc = ga.l[l].dwc;
+    }
+    return c;
+}
+
 // s_l = W_l(d) * norm_l (and t_l = dW_l/dd / d * norm_l) for every layer, evaluated once per distinct
-// (kernel, dis_norm); everything about the layer list is a compile-time constant.
-template <typename SG, bool WITH_T>
-__device__ __forceinline__ void layer_scales(const GroupArgs& ga, const SphF& sp, float d, float d2,
+// (kernel, dis_norm); everything about the layer list is a compile-time constant.  GA: GroupArgs or
+// LayerCoef (anything with .l[l].wc / .dwc).
+template <typename SG, bool WITH_T, typename GA>
+__device__ __forceinline__ void layer_scales(const GA& ga, const SphF& sp, float d, float d2,
                                              float inv, bool pos, float* s, float* t)
 {
 #pragma unroll
@@ -579,24 +598,38 @@ struct TileUnit {
     }
 };
 
-// Calls body(slot) for every list entry of this lane's share of its query's list (sentinel slots
-// included: they fail every radius test).  Units are prefetched one ahead.
+// Calls body(slot * 16) -- list entries are stored as byte offsets into a record plane -- for every list
+// entry of this lane's share of its query's list (sentinel slots included: they fail every radius
+// test).  Units are prefetched SPNB_TILE_PF ahead.
+#ifndef SPNB_TILE_PF
+#define SPNB_TILE_PF 1  // list units fetched ahead of the one being consumed
+#endif
+// 1: no branch around the pair math (an out-of-radius / sentinel pair contributes through zeroed kernel
+// values); lets the compiler overlap the shared-memory gathers of later entries with the math of earlier ones
+#ifndef SPNB_TILE_BRANCHFREE
+#define SPNB_TILE_BRANCHFREE 1
+#endif
 template <int G, typename Body>
 __device__ __forceinline__ void tile_walk(const unsigned char* __restrict__ my_units, int nunits, Body body)
 {
+    constexpr int PF = SPNB_TILE_PF;
     const int wmax = __reduce_max_sync(0xffffffffu, nunits);
-    TileUnit<G> cur, nxt;
-    cur.clear();
-    if (0 < nunits) cur.load(my_units);
+    TileUnit<G> q[PF + 1];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+        q[i].clear();
+        if (i < nunits) q[i].load(my_units + (size_t)i * 256);
+    }
     for (int u = 0; u < wmax; ++u) {
-        nxt.clear();
-        if (u + 1 < nunits) nxt.load(my_units + (size_t)(u + 1) * 256);
+        q[PF].clear();
+        if (u + PF < nunits) q[PF].load(my_units + (size_t)(u + PF) * 256);
 #pragma unroll
         for (int i = 0; i < TileUnit<G>::WORDS; ++i) {
-            body(cur.w[i] & 0xffffu);
-            body(cur.w[i] >> 16);
+            body(q[0].w[i] & 0xffffu);
+            body(q[0].w[i] >> 16);
         }
-        cur = nxt;
+#pragma unroll
+        for (int i = 0; i < PF; ++i) q[i] = q[i + 1];
     }
 }
 
@@ -638,6 +671,8 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     for (int i = 0; i < CT; ++i) G_[i] = 0.0f;
     mbar_wait(&s_bar, 0);
 
+    const LayerCoef<SG::NL> co = load_coef<SG>(ga);
+    const float rad2 = ga.rad2;
     auto pair = [&](const float* r) {
         float d2 = 0.0f;
 #pragma unroll
@@ -645,17 +680,22 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
             const float nr = x[k] - r[k];
             d2 += nr * nr;
         }
-        if (d2 < ga.rad2) {
+        const bool in = d2 < rad2;
+        if (SPNB_TILE_BRANCHFREE || in) {
             const bool pos = d2 > 0.0f;
-            const float inv = fast_rsqrt(d2);
-            const float d = pos ? d2 * inv : 0.0f;
+            const float dd = SPNB_TILE_BRANCHFREE ? fminf(d2, rad2) : d2;  // keeps the sentinel's 1e36 out of W
+            const float inv = fast_rsqrt(dd);
+            const float d = pos ? dd * inv : 0.0f;
             float s[SG::NL];
-            layer_scales<SG, false>(ga, sp, d, d2, inv, pos, s, nullptr);
+            layer_scales<SG, false>(co, sp, d, dd, inv, pos, s, nullptr);
 #pragma unroll
-            for (int l = 0; l < SG::NL; ++l)
+            for (int l = 0; l < SG::NL; ++l) {
+                if (SPNB_TILE_BRANCHFREE && SG::SAL(l) == l) s[l] = in ? s[l] : 0.0f;
+                if (SPNB_TILE_BRANCHFREE && SG::SAL(l) != l) s[l] = s[SG::SAL(l)];
 #pragma unroll
                 for (int c = 0; c < SG::C(l); ++c)
                     G_[SG::chan_off(l) + c] = fmaf(s[l], r[SG::data_off(l) + c], G_[SG::chan_off(l) + c]);
+            }
         }
     };
     if (s_desc.total + 1 <= kTileCap) {
@@ -663,7 +703,7 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
             float r[V * 4];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const float4 t = s_rec[v * kTileCap + slot];
+                const float4 t = *reinterpret_cast<const float4*>(s_raw + v * (kTileCap * 16) + slot);
                 r[4 * v] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
             }
             pair(r);
@@ -671,7 +711,7 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     } else {
         tile_walk<G>(my_units, nunits, [&](unsigned slot) {
             if (slot == 0) return;
-            const size_t j = (size_t)b * N + tile_slot_to_index(s_desc, slot);
+            const size_t j = (size_t)b * N + tile_slot_to_index(s_desc, slot >> 4);
             float r[V * 4];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -738,6 +778,8 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     for (int i = 0; i < CT; ++i) a_dd[i] = 0.0f;
     mbar_wait(&s_bar, 0);
 
+    const LayerCoef<SG::NL> co = load_coef<SG>(ga);
+    const float rad2 = ga.rad2;
     auto pair = [&](const float* r) {
         float disp[D];
         float d2 = 0.0f;
@@ -746,12 +788,21 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
             disp[k] = me[k] - r[k];
             d2 += disp[k] * disp[k];
         }
-        if (d2 < ga.rad2) {
+        const bool in = d2 < rad2;
+        if (SPNB_TILE_BRANCHFREE || in) {
             const bool pos = d2 > 0.0f;
-            const float inv = fast_rsqrt(d2);
-            const float d = pos ? d2 * inv : 0.0f;
+            const float dd = SPNB_TILE_BRANCHFREE ? fminf(d2, rad2) : d2;  // keeps the sentinel's 1e36 out of W
+            const float inv = fast_rsqrt(dd);
+            const float d = pos ? dd * inv : 0.0f;
             float s[SG::NL], t[SG::NL];
-            layer_scales<SG, true>(ga, sp, d, d2, inv, pos, s, t);
+            layer_scales<SG, true>(co, sp, d, dd, inv, pos, s, t);
+            if (SPNB_TILE_BRANCHFREE) {
+#pragma unroll
+                for (int l = 0; l < SG::NL; ++l) {
+                    s[l] = SG::SAL(l) == l ? (in ? s[l] : 0.0f) : s[SG::SAL(l)];
+                    t[l] = SG::SAL(l) == l ? (in ? t[l] : 0.0f) : t[SG::SAL(l)];
+                }
+            }
             float T = 0.0f;
 #pragma unroll
             for (int l = 0; l < SG::NL; ++l) {
@@ -774,7 +825,7 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
             float r[V * 4];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const float4 t = s_rec[v * kTileCap + slot];
+                const float4 t = *reinterpret_cast<const float4*>(s_raw + v * (kTileCap * 16) + slot);
                 r[4 * v] = t.x; r[4 * v + 1] = t.y; r[4 * v + 2] = t.z; r[4 * v + 3] = t.w;
             }
             pair(r);
@@ -782,7 +833,7 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     } else {
         tile_walk<G>(my_units, nunits, [&](unsigned slot) {
             if (slot == 0) return;
-            const size_t j = (size_t)b * N + tile_slot_to_index(s_desc, slot);
+            const size_t j = (size_t)b * N + tile_slot_to_index(s_desc, slot >> 4);
             float r[V * 4];
 #pragma unroll
             for (int v = 0; v < V; ++v) {

@@ -708,10 +708,11 @@ k_tile_build(const float* __restrict__ coll, const TileDesc* __restrict__ descs,
 #pragma unroll
                 for (int t = 1; t < kTileMaxRanges; ++t) g += idx >= st[t];
                 loc = (unsigned)(idx + s_fwd[g]);
-                if ((unsigned)(idx - st[g]) >= (unsigned)s_len[g] || loc > 0xffffu) {
-                    bad = true;  // not in the block's ranges, or the slot does not fit 16 bits
+                if ((unsigned)(idx - st[g]) >= (unsigned)s_len[g] || loc > 0xfffu) {
+                    bad = true;  // not in the block's ranges, or slot * 16 does not fit 16 bits
                     loc = 0;
                 }
+                loc <<= 4;  // entries are byte offsets into a plane of 16-byte record quarters
             }
             if (lane < ((take + kTileUnit - 1) & ~(kTileUnit - 1)) && k < K)
                 trow[(k >> 4) * 128 + (k & 15)] = (unsigned short)loc;

@@ -12,8 +12,9 @@
 //    ranges are merged into disjoint ascending ones and stored in a TileDesc; a ConvSP kernel stages
 //    them into shared memory with a handful of TMA bulk copies (cp.async.bulk) and then only gathers
 //    from shared memory;
-//  * a list entry is the 16-bit position of the neighbour inside that staged tile (0 = sentinel, a
-//    record placed far outside every radius), 2 bytes instead of 4;
+//  * a list entry is the 16-bit position of the neighbour inside that staged tile, stored times 16
+//    (the byte offset of its record quarter in a shared-memory plane; 0 = sentinel, a record placed
+//    far outside every radius), 2 bytes instead of 4;
 //  * entries are stored in 32-byte UNITS of 16 entries, interleaved over the 8 queries of a row group
 //    so that a warp reads whole 256-byte lines whether it spends 1, 2 or 4 lanes per query:
 //        addr(b, tb, ql, k) = lists + (((b*ntb + tb)*8 + ql/8) * (K/16) + k/16) * 256 + (ql%8)*32 + (k%16)*2
@@ -30,7 +31,7 @@
 //
 // flag (first int of the buffer) != 0 marks the sidecar unusable for this call: bit 0 = a list is full,
 // i.e. may have been cut at K (the symmetric backward is then invalid, see convsp_group.cu), bit 1 = a
-// neighbour lies outside the block's ranges or a tile has more than 65535 records.  Consumers test it on the DEVICE and the ordinary list walk runs instead, so nothing
+// neighbour lies outside the block's ranges or a tile has more than 4095 records.  Consumers test it on the DEVICE and the ordinary list walk runs instead, so nothing
 // depends on a host synchronisation.
 #pragma once
 #include <stddef.h>
@@ -38,11 +39,15 @@
 
 namespace spnb {
 
-constexpr int kTileQ = 64;          // queries per tile block
+#ifndef SPNB_TILE_Q
+#define SPNB_TILE_Q 64
+#endif
+constexpr int kTileQ = SPNB_TILE_Q;  // queries per tile block (a multiple of 64)
 #ifndef SPNB_TILE_CAP
 #define SPNB_TILE_CAP 1024
 #endif
 constexpr int kTileCap = SPNB_TILE_CAP;  // staged records per tile, including the sentinel at slot 0
+static_assert(kTileCap <= 4096, "entries are slot * 16 in 16 bits");
 constexpr int kTileMaxRanges = 9;   // 3^(D-1) for D <= 3
 constexpr int kTileUnit = 16;       // entries per 32-byte unit
 constexpr int kTileMaxNdim = 3;
@@ -81,10 +86,10 @@ __host__ __device__ inline bool tile_lists_supported(int N, int D, int K)
     return D >= 1 && D <= kTileMaxNdim && K >= kTileUnit && (K % kTileUnit) == 0 && N >= 1;
 }
 
-// byte offset of entry k of query ql (0..63) of tile block (b, tb), relative to the list area
+// byte offset of entry k of query ql (0..kTileQ-1) of tile block (b, tb), relative to the list area
 __host__ __device__ inline size_t tile_entry_off(int ntb, int K, int b, int tb, int ql, int k)
 {
-    return ((((size_t)b * ntb + tb) * 8 + (ql >> 3)) * (size_t)(K / kTileUnit) + (k / kTileUnit)) * 256 +
+    return ((((size_t)b * ntb + tb) * (kTileQ / 8) + (ql >> 3)) * (size_t)(K / kTileUnit) + (k / kTileUnit)) * 256 +
            (size_t)(ql & 7) * 32 + (size_t)(k % kTileUnit) * 2;
 }
 

@@ -34,7 +34,7 @@ def decode(tiles, B, N, K):
     desc = raw[lay["desc_off"]:lay["cnt_off"]].view(np.int32).reshape(B, ntb, DESC_INTS)
     counts = raw[lay["cnt_off"]:lay["cnt_off"] + 4 * B * N].view(np.int32).reshape(B, N)
     # lists[b, tb, rowgroup, unit, slot-in-rowgroup, entry]
-    lists = raw[lay["list_off"]:].view(np.uint16).reshape(B, ntb, 8, K // TILE_UNIT, 8, TILE_UNIT)
+    lists = raw[lay["list_off"]:].view(np.uint16).reshape(B, ntb, TILE_Q // 8, K // TILE_UNIT, 8, TILE_UNIT)
     out = -np.ones((B, N, K), dtype=np.int64)
     for b in range(B):
         for tb in range(ntb):
@@ -50,6 +50,8 @@ def decode(tiles, B, N, K):
                 n = tb * TILE_Q + ql
                 c = int(counts[b, n])
                 ent = lists[b, tb, ql // 8, :, ql % 8, :].reshape(-1)
+                assert ((ent & 15) == 0).all(), "entries are slot * 16"
+                ent = ent >> 4
                 cpad = (c + TILE_UNIT - 1) // TILE_UNIT * TILE_UNIT
                 assert (ent[c:cpad] == 0).all(), "tail of the last unit must hold the sentinel"
                 out[b, n, :c] = slot2idx[ent[:c]]
