@@ -607,12 +607,13 @@ struct TileUnit {
 // 1: no branch around the pair math (an out-of-radius / sentinel pair contributes through zeroed kernel
 // values); lets the compiler overlap the shared-memory gathers of later entries with the math of earlier ones
 #ifndef SPNB_TILE_BRANCHFREE
-#define SPNB_TILE_BRANCHFREE 1
+#define SPNB_TILE_BRANCHFREE 0
 #endif
 template <int G, typename Body>
-__device__ __forceinline__ void tile_walk(const unsigned char* __restrict__ my_units, int nunits, Body body)
+__device__ __forceinline__ void tile_walk(const unsigned char* __restrict__ my_units, int cnt, Body body)
 {
     constexpr int PF = SPNB_TILE_PF;
+    const int nunits = (cnt + kTileUnit - 1) / kTileUnit;
     const int wmax = __reduce_max_sync(0xffffffffu, nunits);
     TileUnit<G> q[PF + 1];
 #pragma unroll
@@ -623,10 +624,19 @@ __device__ __forceinline__ void tile_walk(const unsigned char* __restrict__ my_u
     for (int u = 0; u < wmax; ++u) {
         q[PF].clear();
         if (u + PF < nunits) q[PF].load(my_units + (size_t)(u + PF) * 256);
+        // even words: entries 0..7 of the unit (4x4-transposed storage, tile_lists.cuh)
 #pragma unroll
-        for (int i = 0; i < TileUnit<G>::WORDS; ++i) {
+        for (int i = 0; i < TileUnit<G>::WORDS; i += 2) {
             body(q[0].w[i] & 0xffffu);
             body(q[0].w[i] >> 16);
+        }
+        // odd words: entries 8..15 -- skipped when no query of the warp has that many left
+        if (__any_sync(0xffffffffu, cnt - u * kTileUnit > kTileUnit / 2)) {
+#pragma unroll
+            for (int i = 1; i < TileUnit<G>::WORDS; i += 2) {
+                body(q[0].w[i] & 0xffffu);
+                body(q[0].w[i] >> 16);
+            }
         }
 #pragma unroll
         for (int i = 0; i < PF; ++i) q[i] = q[i + 1];
@@ -664,7 +674,6 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
         for (int k = 0; k < D; ++k) x[k] = t[k];
     }
     const int cnt = active ? ta.counts[q] : 0;
-    const int nunits = (cnt + kTileUnit - 1) / kTileUnit;
     const unsigned char* my_units = ta.lists + tile_entry_off(ta.ntb, K, b, tb, ql, 0) + sub * (32 / G);
     float G_[CT];
 #pragma unroll
@@ -699,7 +708,7 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
         }
     };
     if (s_desc.total + 1 <= kTileCap) {
-        tile_walk<G>(my_units, nunits, [&](unsigned slot) {
+        tile_walk<G>(my_units, cnt, [&](unsigned slot) {
             float r[V * 4];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -709,7 +718,7 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
             pair(r);
         });
     } else {
-        tile_walk<G>(my_units, nunits, [&](unsigned slot) {
+        tile_walk<G>(my_units, cnt, [&](unsigned slot) {
             if (slot == 0) return;
             const size_t j = (size_t)b * N + tile_slot_to_index(s_desc, slot >> 4);
             float r[V * 4];
@@ -769,7 +778,6 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
         me[4 * v] = t.x; me[4 * v + 1] = t.y; me[4 * v + 2] = t.z; me[4 * v + 3] = t.w;
     }
     const int cnt = active ? ta.counts[q] : 0;
-    const int nunits = (cnt + kTileUnit - 1) / kTileUnit;
     const unsigned char* my_units = ta.lists + tile_entry_off(ta.ntb, K, b, tb, ql, 0) + sub * (32 / G);
     float a_dl[D], a_dd[CT];
 #pragma unroll
@@ -821,7 +829,7 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
         }
     };
     if (s_desc.total + 1 <= kTileCap) {
-        tile_walk<G>(my_units, nunits, [&](unsigned slot) {
+        tile_walk<G>(my_units, cnt, [&](unsigned slot) {
             float r[V * 4];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
@@ -831,7 +839,7 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
             pair(r);
         });
     } else {
-        tile_walk<G>(my_units, nunits, [&](unsigned slot) {
+        tile_walk<G>(my_units, cnt, [&](unsigned slot) {
             if (slot == 0) return;
             const size_t j = (size_t)b * N + tile_slot_to_index(s_desc, slot >> 4);
             float r[V * 4];

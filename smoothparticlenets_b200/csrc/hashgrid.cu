@@ -715,7 +715,7 @@ k_tile_build(const float* __restrict__ coll, const TileDesc* __restrict__ descs,
                 loc <<= 4;  // entries are byte offsets into a plane of 16-byte record quarters
             }
             if (lane < ((take + kTileUnit - 1) & ~(kTileUnit - 1)) && k < K)
-                trow[(k >> 4) * 128 + (k & 15)] = (unsigned short)loc;
+                trow[(k >> 4) * 128 + ((k & 3) * 4 + ((k >> 2) & 3))] = (unsigned short)loc;  // 4x4-transposed unit
             cnt += take;
             if (take < 32) break;
         }

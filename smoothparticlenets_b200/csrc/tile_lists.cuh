@@ -18,6 +18,10 @@
 //  * entries are stored in 32-byte UNITS of 16 entries, interleaved over the 8 queries of a row group
 //    so that a warp reads whole 256-byte lines whether it spends 1, 2 or 4 lanes per query:
 //        addr(b, tb, ql, k) = lists + (((b*ntb + tb)*8 + ql/8) * (K/16) + k/16) * 256 + (ql%8)*32 + (k%16)*2
+//    Inside a unit the 16 entries are stored 4x4-transposed (entry e at position (e%4)*4 + e/4), so
+//    that whatever the number of lanes per query, every lane's EVEN 32-bit words hold entries 0..7 of
+//    the unit and its ODD words entries 8..15: a warp skips the odd words of a unit when none of its
+//    queries has more than 8 entries left (most lists end in the first half of their last unit).
 //    The tail of a query's last unit is filled with the sentinel; units past it are never read
 //    (counts[b][n] holds the list length).
 //
@@ -89,8 +93,9 @@ __host__ __device__ inline bool tile_lists_supported(int N, int D, int K)
 // byte offset of entry k of query ql (0..kTileQ-1) of tile block (b, tb), relative to the list area
 __host__ __device__ inline size_t tile_entry_off(int ntb, int K, int b, int tb, int ql, int k)
 {
+    const int e = k % kTileUnit;
     return ((((size_t)b * ntb + tb) * (kTileQ / 8) + (ql >> 3)) * (size_t)(K / kTileUnit) + (k / kTileUnit)) * 256 +
-           (size_t)(ql & 7) * 32 + (size_t)(k % kTileUnit) * 2;
+           (size_t)(ql & 7) * 32 + (size_t)((e & 3) * 4 + (e >> 2)) * 2;
 }
 
 }  // namespace spnb

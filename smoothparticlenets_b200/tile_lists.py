@@ -49,10 +49,11 @@ def decode(tiles, B, N, K):
             for ql in range(min(TILE_Q, N - tb * TILE_Q)):
                 n = tb * TILE_Q + ql
                 c = int(counts[b, n])
-                ent = lists[b, tb, ql // 8, :, ql % 8, :].reshape(-1)
-                assert ((ent & 15) == 0).all(), "entries are slot * 16"
-                ent = ent >> 4
+                ent = lists[b, tb, ql // 8, :, ql % 8, :]
+                ent = ent.reshape(-1, 4, 4).transpose(0, 2, 1).reshape(-1)  # units are stored 4x4-transposed
                 cpad = (c + TILE_UNIT - 1) // TILE_UNIT * TILE_UNIT
+                assert ((ent[:cpad] & 15) == 0).all(), "entries are slot * 16"
+                ent = ent >> 4
                 assert (ent[c:cpad] == 0).all(), "tail of the last unit must hold the sentinel"
                 out[b, n, :c] = slot2idx[ent[:c]]
     return flag, counts, out, int(desc[:, :, 1].max())
