@@ -652,9 +652,13 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     float4* s_rec = reinterpret_cast<float4*>(s_raw);
     __shared__ TileDesc s_desc;
     __shared__ __align__(8) unsigned long long s_bar;
-    if (*ta.flag != 0) return;
     const int tid = threadIdx.x, tb = blockIdx.x, b = blockIdx.y;
-    if (tid < 32) reinterpret_cast<int*>(&s_desc)[tid] = reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb)[tid];
+    // the descriptor load is issued together with the flag load (both are inputs of this call's
+    // predecessors only), so the flag test does not add a global-memory latency to the prologue
+    int desc_word = 0;
+    if (tid < 32) desc_word = __ldg(reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb) + tid);
+    if (*ta.flag != 0) return;
+    if (tid < 32) reinterpret_cast<int*>(&s_desc)[tid] = desc_word;
     if (tid == 0) mbar_init(&s_bar, 1);
     if (tid < V) s_rec[tid * kTileCap] = tid == 0 ? make_float4(1e18f, 1e18f, 1e18f, 0.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     __syncthreads();
@@ -757,9 +761,13 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     float4* s_rec = reinterpret_cast<float4*>(s_raw);
     __shared__ TileDesc s_desc;
     __shared__ __align__(8) unsigned long long s_bar;
-    if (*ta.flag != 0) return;
     const int tid = threadIdx.x, tb = blockIdx.x, b = blockIdx.y;
-    if (tid < 32) reinterpret_cast<int*>(&s_desc)[tid] = reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb)[tid];
+    // the descriptor load is issued together with the flag load (both are inputs of this call's
+    // predecessors only), so the flag test does not add a global-memory latency to the prologue
+    int desc_word = 0;
+    if (tid < 32) desc_word = __ldg(reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb) + tid);
+    if (*ta.flag != 0) return;
+    if (tid < 32) reinterpret_cast<int*>(&s_desc)[tid] = desc_word;
     if (tid == 0) mbar_init(&s_bar, 1);
     if (tid < V) s_rec[tid * kTileCap] = tid == 0 ? make_float4(1e18f, 1e18f, 1e18f, 0.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     __syncthreads();

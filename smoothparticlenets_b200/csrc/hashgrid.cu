@@ -689,6 +689,15 @@ k_tile_build(const float* __restrict__ coll, const TileDesc* __restrict__ descs,
 
     bool bad = false, cut = false;
     constexpr int RPW = kTileQ / (kBuildThreads / 32);  // rows per warp
+    // the first 128-byte chunk of all of the warp's rows is requested up front (independent loads in
+    // flight); most lists end inside it, the rest continue chunk by chunk
+    float first[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        const int m = tb * kTileQ + warp * RPW + r;
+        first[r] = (m < N && lane < K) ? coll[((size_t)b * N + m) * K + lane] : -1.0f;
+    }
+#pragma unroll
     for (int r = 0; r < RPW; ++r) {
         const int ql = warp * RPW + r;
         const int m = tb * kTileQ + ql;
@@ -698,7 +707,7 @@ k_tile_build(const float* __restrict__ coll, const TileDesc* __restrict__ descs,
         int cnt = 0;
         for (int base = 0; base < K; base += 32) {
             const int k = base + lane;
-            const float f = k < K ? row[k] : -1.0f;
+            const float f = base == 0 ? first[r] : (k < K ? row[k] : -1.0f);
             const unsigned neg = __ballot_sync(0xffffffffu, !(f >= 0.0f));
             const int take = neg ? __ffs(neg) - 1 : 32;  // entries before the terminator
             unsigned loc = 0;                            // lanes past it write the sentinel padding
