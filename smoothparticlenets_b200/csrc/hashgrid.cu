@@ -509,7 +509,10 @@ k_tile_ranges(const uint32_t* __restrict__ keys, const float* __restrict__ grid_
 // coalesced row writes, -1 padding.  Cells are visited in the reference's odometer order over
 // {-1,0,1}^D with dimension 0 fastest and candidates inside a cell in sorted order
 // (common_funcs.h:906-943), so rows are bit-identical to the reference's, truncation included.
-constexpr int kQPW = 8;          // queries per warp
+#ifndef SPNB_COLLIDE_QPW
+#define SPNB_COLLIDE_QPW 16  // measured: 8 -> 318 us, 16 -> 304 us, 32 -> 306 us at c2 (longer same-cell runs share one candidate staging)
+#endif
+constexpr int kQPW = SPNB_COLLIDE_QPW;  // queries per warp (<= 32)
 constexpr int kCollideWarps = 8;  // warps per block
 
 template <int DT>
