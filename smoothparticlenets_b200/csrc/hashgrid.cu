@@ -664,9 +664,10 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
 
 // ---- tile lists (tile_lists.cuh) ---------------------------------------------------------------------
 // One block per tile block of 64 queries, run after k_collide on the float rows it wrote: every warp
-// reads the rows of 8 queries (coalesced 128-byte chunks up to the terminator), maps each neighbour
-// index to its slot in the block's candidate ranges (TileDesc: ascending range starts kept in
-// registers) and writes the 16-bit entry, the sentinel padding of the last unit and the list length.
+// reads the rows of 8 queries (four rows at a time, 128 bytes of each per step, up to the terminator),
+// maps each neighbour index to its slot in the block's candidate ranges (TileDesc: ascending range
+// starts kept in registers) and writes the 16-bit entry, the sentinel padding of the last unit and the
+// list length.
 constexpr int kBuildThreads = 256;
 
 __global__ void __launch_bounds__(kBuildThreads)
@@ -692,49 +693,70 @@ k_tile_build(const float* __restrict__ coll, const TileDesc* __restrict__ descs,
 
     bool bad = false, cut = false;
     constexpr int RPW = kTileQ / (kBuildThreads / 32);  // rows per warp
-    // the first 128-byte chunk of all of the warp's rows is requested up front (independent loads in
-    // flight); most lists end inside it, the rest continue chunk by chunk
-    float first[RPW];
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-        const int m = tb * kTileQ + warp * RPW + r;
-        first[r] = (m < N && lane < K) ? coll[((size_t)b * N + m) * K + lane] : -1.0f;
-    }
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-        const int ql = warp * RPW + r;
+    static_assert(RPW % 4 == 0, "rows are processed four at a time");
+    // The kernel is issue-bound (ncu: 86 % issue active), so a warp works on FOUR rows at once: 8 lanes per
+    // row, each lane one float4 = 4 entries, i.e. 32 entries per row and step with a quarter of the
+    // per-row control instructions.  The row ends at its first negative entry (common_funcs.h:476).
+    const int grp = lane >> 3, sub = lane & 7;
+    const bool wide = (K & 3) == 0 && (reinterpret_cast<size_t>(coll) & 15) == 0;
+#pragma unroll 1
+    for (int r0 = 0; r0 < RPW; r0 += 4) {
+        const int ql = warp * RPW + r0 + grp;
         const int m = tb * kTileQ + ql;
-        if (m >= N) break;
-        const float* row = coll + ((size_t)b * N + m) * K;
+        const bool live_row = m < N;
+        const float* row = coll + ((size_t)b * N + (live_row ? m : 0)) * K;
         unsigned short* trow = tlists + tile_entry_off(ntb, K, b, tb, ql, 0) / 2;
         int cnt = 0;
+        bool open = live_row;  // terminator not seen yet
         for (int base = 0; base < K; base += 32) {
-            const int k = base + lane;
-            const float f = base == 0 ? first[r] : (k < K ? row[k] : -1.0f);
-            const unsigned neg = __ballot_sync(0xffffffffu, !(f >= 0.0f));
-            const int take = neg ? __ffs(neg) - 1 : 32;  // entries before the terminator
-            unsigned loc = 0;                            // lanes past it write the sentinel padding
-            if (lane < take) {
-                const int idx = (int)f;
-                int g = 0;
+            if (!__any_sync(0xffffffffu, open)) break;
+            const int k0 = base + sub * 4;
+            float f[4] = {-1.0f, -1.0f, -1.0f, -1.0f};
+            if (open) {
+                if (wide && k0 + 3 < K) {
+                    const float4 v = *reinterpret_cast<const float4*>(row + k0);
+                    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+                } else {
 #pragma unroll
-                for (int t = 1; t < kTileMaxRanges; ++t) g += idx >= st[t];
-                loc = (unsigned)(idx + s_fwd[g]);
-                if ((unsigned)(idx - st[g]) >= (unsigned)s_len[g] || loc > 0xfffu) {
-                    bad = true;  // not in the block's ranges, or slot * 16 does not fit 16 bits
-                    loc = 0;
+                    for (int j = 0; j < 4; ++j)
+                        if (k0 + j < K) f[j] = row[k0 + j];
                 }
-                loc <<= 4;  // entries are byte offsets into a plane of 16-byte record quarters
             }
-            if (lane < ((take + kTileUnit - 1) & ~(kTileUnit - 1)) && k < K)
-                trow[(k >> 4) * 128 + ((k & 3) * 4 + ((k >> 2) & 3))] = (unsigned short)loc;  // 4x4-transposed unit
+            int nv = 0;  // length of the run of non-negative entries that starts at f[0]
+#pragma unroll
+            for (int j = 3; j >= 0; --j) nv = f[j] >= 0.0f ? nv + 1 : 0;
+            const unsigned fullm = (__ballot_sync(0xffffffffu, nv == 4) >> (grp * 8)) & 0xffu;
+            const int l0 = fullm == 0xffu ? 8 : __ffs(~fullm) - 1;         // first lane of the group with a terminator
+            const int nv0 = __shfl_sync(0xffffffffu, nv, grp * 8 + (l0 & 7));
+            const int take = open ? (l0 == 8 ? 32 : l0 * 4 + nv0) : 0;    // entries before the terminator
+            const int padded = (take + kTileUnit - 1) & ~(kTileUnit - 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = sub * 4 + j;  // entry within this step's 32
+                unsigned loc = 0;           // entries past the terminator: sentinel padding of the last unit
+                if (e < take) {
+                    const int idx = (int)f[j];
+                    int g = 0;
+#pragma unroll
+                    for (int t = 1; t < kTileMaxRanges; ++t) g += idx >= st[t];
+                    loc = (unsigned)(idx + s_fwd[g]);
+                    if ((unsigned)(idx - st[g]) >= (unsigned)s_len[g] || loc > 0xfffu) {
+                        bad = true;  // not in the block's ranges, or slot * 16 does not fit 16 bits
+                        loc = 0;
+                    }
+                    loc <<= 4;  // entries are byte offsets into a plane of 16-byte record quarters
+                }
+                const int k = base + e;
+                if (open && e < padded && k < K)
+                    trow[(k >> 4) * 128 + ((k & 3) * 4 + ((k >> 2) & 3))] = (unsigned short)loc;  // 4x4-transposed unit
+            }
             cnt += take;
-            if (take < 32) break;
+            if (take < 32) open = false;
         }
-        if (cnt >= K) cut = true;
-        if (lane == 0) tcounts[(size_t)b * N + m] = cnt;
+        if (live_row && cnt >= K) cut = true;
+        if (live_row && sub == 0) tcounts[(size_t)b * N + m] = cnt;
     }
-    if (cut && lane == 0) atomicOr(tile_flag, 1);
+    if (cut) atomicOr(tile_flag, 1);
     if (bad) atomicOr(tile_flag, 2);
 }
 
