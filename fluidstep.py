@@ -107,9 +107,12 @@ class FluidStep(nn.Module):
     def forward(self, locs, vel):
         dt = DT
         ones = torch.ones(locs.shape[:-1] + (1,), device=locs.device, dtype=locs.dtype)
-        vel = vel + self.gravity * dt
-        vel = self._cap_magnitude(vel, self.max_speed)
-        new_locs = locs + vel * dt
+        if self.pbf is not None and hasattr(self.pbf, "pbf_integrate"):
+            vel, new_locs = self.pbf.pbf_integrate(locs, vel, GRAVITY[:self.ndim], dt, self.max_speed)
+        else:
+            vel = vel + self.gravity * dt
+            vel = self._cap_magnitude(vel, self.max_speed)
+            new_locs = locs + vel * dt
         new_locs, vel, pidxs, neighbors = self.coll(new_locs, vel)
         for _ in range(NUM_ITERATIONS if self.pbf is not None else 0):
             # same data flow as below; the elementwise arithmetic between the groups in three fused stages
@@ -162,14 +165,19 @@ class FluidStep(nn.Module):
             scale = self.relu(scale - DAMP) + DAMP
             delta = delta / scale
             new_locs = new_locs + delta
-        vel = (new_locs - self.reorder_un2sort(pidxs, locs)) / dt
-        if self.fused:
+        if self.pbf is not None and hasattr(self.pbf, "pbf_velocity"):
+            vel = self.pbf.pbf_velocity(new_locs, self.reorder_un2sort(pidxs, locs), dt)
             vj, vi_s = self.group_v(new_locs, [vel, ones], neighbors)
-            vi = vel * vi_s
+            vel = self.pbf.pbf_viscosity(vel, vj, vi_s, dt * VISCOSITY / self.density_rest)
         else:
-            vj = self.spikyD(new_locs, vel, neighbors)
-            vi = vel * self.spiky1(new_locs, ones, neighbors)
-        vel = vel + dt * VISCOSITY / self.density_rest * (vj - vi)
+            vel = (new_locs - self.reorder_un2sort(pidxs, locs)) / dt
+            if self.fused:
+                vj, vi_s = self.group_v(new_locs, [vel, ones], neighbors)
+                vi = vel * vi_s
+            else:
+                vj = self.spikyD(new_locs, vel, neighbors)
+                vi = vel * self.spiky1(new_locs, ones, neighbors)
+            vel = vel + dt * VISCOSITY / self.density_rest * (vj - vi)
         new_locs, vel = self.reorder_sort2un(pidxs, new_locs, vel)
         return new_locs, vel
 

@@ -199,6 +199,20 @@ int spnb_pbf_stage3_backward(const float* d0, const float* cd, const float* nrm,
                              const float* g, float* g_d0, float* g_nrm, float* g_ncount, long long BN,
                              int ndims, float relaxation, float damp, void* stream);
 
+/* The ends of the step (fluid_sim.py:355-365, 412-424): gravity + velocity cap + position update
+ * (gravity: HOST array of ndims floats), velocity from the position change ((a - b) / dt; backward != 0:
+ * o = a / dt and, when o2 != NULL, o2 = -(a / dt)), and the XSPH viscosity update w0 + c*(vj - w0*vi_s). */
+int spnb_pbf_integrate_forward(const float* x, const float* v, float* v2, float* x1, long long BN, int ndims,
+                               const float* gravity_host, float dt, float cap, void* stream);
+int spnb_pbf_integrate_backward(const float* v, const float* g_v2, const float* g_x1, float* g_v, long long BN,
+                                int ndims, const float* gravity_host, float dt, float cap, void* stream);
+int spnb_pbf_velocity(const float* a, const float* b, float* o, float* o2, long long n_floats, float dt,
+                      int backward, void* stream);
+int spnb_pbf_viscosity_forward(const float* w0, const float* vj, const float* vi_s, float* w1, long long BN,
+                               int ndims, float c, void* stream);
+int spnb_pbf_viscosity_backward(const float* w0, const float* vi_s, const float* g, float* g_w0, float* g_vj,
+                                float* g_vi_s, long long BN, int ndims, float c, void* stream);
+
 /* ---- ConvSDF ---------------------------------------------------------------------------------- */
 
 /* Forward (bias added in the kernel, as common_funcs.h:834-835).  Replaces cuda_convsdf with NULL

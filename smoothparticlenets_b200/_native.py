@@ -40,6 +40,11 @@ _SIGNATURES = {
     "spnb_pbf_stage2_backward": (_i, [_vp] * 14 + [ctypes.c_longlong, _i, _f, _f, _f, _f, _f, _vp]),
     "spnb_pbf_stage3_forward": (_i, [_vp] * 6 + [ctypes.c_longlong, _i, _f, _f, _vp]),
     "spnb_pbf_stage3_backward": (_i, [_vp] * 8 + [ctypes.c_longlong, _i, _f, _f, _vp]),
+    "spnb_pbf_integrate_forward": (_i, [_vp] * 4 + [ctypes.c_longlong, _i, ctypes.POINTER(_f), _f, _f, _vp]),
+    "spnb_pbf_integrate_backward": (_i, [_vp] * 4 + [ctypes.c_longlong, _i, ctypes.POINTER(_f), _f, _f, _vp]),
+    "spnb_pbf_velocity": (_i, [_vp] * 4 + [ctypes.c_longlong, _f, _i, _vp]),
+    "spnb_pbf_viscosity_forward": (_i, [_vp] * 4 + [ctypes.c_longlong, _i, _f, _vp]),
+    "spnb_pbf_viscosity_backward": (_i, [_vp] * 6 + [ctypes.c_longlong, _i, _f, _vp]),
     "spnb_convsdf_forward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp, _i, _vp,
                                   _vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "spnb_convsdf_backward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp, _i, _vp,

@@ -179,6 +179,115 @@ k_pbf3_bwd(const float* __restrict__ d0, const float* __restrict__ cd, const flo
     g_ncount[n] = gnc + (act ? gsc / (1.0f + relax) : 0.0f);
 }
 
+// ---- the ends of the step (fluid_sim.py:355-365, 412-424) ----------------------------------------------
+//   integrate:  v1 = v + gravity * dt;  m = -(relu(-cap / (|v1| + 1e-4) + 1) - 1);  v2 = v1 * m;  x1 = x + v2 * dt
+//   velocity :  w0 = (x - xs) / dt                       (new velocity from the position change)
+//   viscosity:  w1 = w0 + c * (vj - w0 * vi_s)           (c = dt * viscosity / rest density)
+struct GVec { float v[3]; };
+
+template <int D>
+__global__ void __launch_bounds__(kGlueThreads)
+k_pbf_integrate_fwd(const float* __restrict__ x, const float* __restrict__ v, float* __restrict__ v2,
+                    float* __restrict__ x1, long long BN, GVec g, float dt, float cap)
+{
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= BN) return;
+    float v1[D], ss = 0.0f;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        v1[c] = v[n * D + c] + g.v[c] * dt;
+        ss += v1[c] * v1[c];
+    }
+    const float s = cap / (sqrtf(ss) + 0.0001f);
+    const float t = -s + 1.0f;
+    const float m = -((t > 0.0f ? t : 0.0f) - 1.0f);
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const float o = v1[c] * m;
+        v2[n * D + c] = o;
+        x1[n * D + c] = x[n * D + c] + o * dt;
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kGlueThreads)
+k_pbf_integrate_bwd(const float* __restrict__ v, const float* __restrict__ g_v2, const float* __restrict__ g_x1,
+                    float* __restrict__ g_v, long long BN, GVec g, float dt, float cap)
+{
+    // d/dx = g_x1: the caller aliases it
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= BN) return;
+    float v1[D], gt[D], ss = 0.0f, dot = 0.0f;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        v1[c] = v[n * D + c] + g.v[c] * dt;
+        ss += v1[c] * v1[c];
+        gt[c] = (g_v2 ? g_v2[n * D + c] : 0.0f) + (g_x1 ? g_x1[n * D + c] * dt : 0.0f);
+        dot += gt[c] * v1[c];
+    }
+    const float nn = sqrtf(ss);
+    const float den = nn + 0.0001f;
+    const float s = cap / den;
+    const float t = -s + 1.0f;
+    const float m = -((t > 0.0f ? t : 0.0f) - 1.0f);
+    // m = s where s < 1 (capped), else 1;  ds/d|v1| = -cap / (|v1| + eps)^2;  d|v1|/dv1 = v1 / |v1|
+    const float k = (t > 0.0f && nn > 0.0f) ? dot * (-cap / (den * den)) / nn : 0.0f;
+#pragma unroll
+    for (int c = 0; c < D; ++c) g_v[n * D + c] = gt[c] * m + k * v1[c];
+}
+
+__global__ void __launch_bounds__(kGlueThreads)
+k_pbf_velocity(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, float* __restrict__ o2,
+               long long n_floats, float dt, int backward)
+{
+    // forward: o = (a - b) / dt;  backward (a = grad): o = a / dt, o2 = -(a / dt)
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_floats) return;
+    if (!backward) {
+        o[i] = (a[i] - b[i]) / dt;
+    } else {
+        const float gq = a[i] / dt;
+        o[i] = gq;
+        if (o2) o2[i] = -gq;
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kGlueThreads)
+k_pbf_viscosity_fwd(const float* __restrict__ w0, const float* __restrict__ vj, const float* __restrict__ vi_s,
+                    float* __restrict__ w1, long long BN, float c)
+{
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= BN) return;
+    const float s = vi_s[n];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const float w = w0[n * D + k];
+        w1[n * D + k] = w + c * (vj[n * D + k] - w * s);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kGlueThreads)
+k_pbf_viscosity_bwd(const float* __restrict__ w0, const float* __restrict__ vi_s, const float* __restrict__ g,
+                    float* __restrict__ g_w0, float* __restrict__ g_vj, float* __restrict__ g_vi_s, long long BN,
+                    float c)
+{
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= BN) return;
+    const float s = vi_s[n];
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const float gv = g[n * D + k];
+        const float gc = gv * c;  // d/d(vj - w0 * vi_s)
+        g_vj[n * D + k] = gc;
+        g_w0[n * D + k] = gv + -gc * s;
+        acc += -gc * w0[n * D + k];
+    }
+    g_vi_s[n] = acc;
+}
+
 }  // namespace
 }  // namespace spnb
 
@@ -282,6 +391,71 @@ int spnb_pbf_stage3_backward(const float* d0, const float* cd, const float* nrm,
     }
     SPNB_GLUE_LAUNCH(k_pbf3_bwd, d0, cd, nrm, ncount, g, g_d0, g_nrm, g_ncount, BN, relaxation, damp);
     return check_launch("spnb_pbf_stage3_backward") ? 1 : 0;
+}
+
+int spnb_pbf_integrate_forward(const float* x, const float* v, float* v2, float* x1, long long BN, int D,
+                               const float* gravity_host, float dt, float cap, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!x || !v || !v2 || !x1 || !gravity_host || BN <= 0) {
+        set_error("spnb_pbf_integrate_forward: bad arguments");
+        return 0;
+    }
+    GVec g = {{0.0f, 0.0f, 0.0f}};
+    for (int c = 0; c < D && c < 3; ++c) g.v[c] = gravity_host[c];
+    SPNB_GLUE_LAUNCH(k_pbf_integrate_fwd, x, v, v2, x1, BN, g, dt, cap);
+    return check_launch("spnb_pbf_integrate_forward") ? 1 : 0;
+}
+
+int spnb_pbf_integrate_backward(const float* v, const float* g_v2, const float* g_x1, float* g_v, long long BN,
+                                int D, const float* gravity_host, float dt, float cap, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!v || !g_v || !gravity_host || BN <= 0) {
+        set_error("spnb_pbf_integrate_backward: bad arguments");
+        return 0;
+    }
+    GVec g = {{0.0f, 0.0f, 0.0f}};
+    for (int c = 0; c < D && c < 3; ++c) g.v[c] = gravity_host[c];
+    SPNB_GLUE_LAUNCH(k_pbf_integrate_bwd, v, g_v2, g_x1, g_v, BN, g, dt, cap);
+    return check_launch("spnb_pbf_integrate_backward") ? 1 : 0;
+}
+
+int spnb_pbf_velocity(const float* a, const float* b, float* o, float* o2, long long n_floats, float dt,
+                      int backward, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!a || !o || (!backward && !b) || n_floats <= 0) {
+        set_error("spnb_pbf_velocity: bad arguments");
+        return 0;
+    }
+    k_pbf_velocity<<<cdiv(n_floats, kGlueThreads), kGlueThreads, 0, stream>>>(a, b, o, o2, n_floats, dt, backward);
+    count_launches(1);
+    return check_launch("spnb_pbf_velocity") ? 1 : 0;
+}
+
+int spnb_pbf_viscosity_forward(const float* w0, const float* vj, const float* vi_s, float* w1, long long BN, int D,
+                               float c, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!w0 || !vj || !vi_s || !w1 || BN <= 0) {
+        set_error("spnb_pbf_viscosity_forward: bad arguments");
+        return 0;
+    }
+    SPNB_GLUE_LAUNCH(k_pbf_viscosity_fwd, w0, vj, vi_s, w1, BN, c);
+    return check_launch("spnb_pbf_viscosity_forward") ? 1 : 0;
+}
+
+int spnb_pbf_viscosity_backward(const float* w0, const float* vi_s, const float* g, float* g_w0, float* g_vj,
+                                float* g_vi_s, long long BN, int D, float c, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!w0 || !vi_s || !g || !g_w0 || !g_vj || !g_vi_s || BN <= 0) {
+        set_error("spnb_pbf_viscosity_backward: bad arguments");
+        return 0;
+    }
+    SPNB_GLUE_LAUNCH(k_pbf_viscosity_bwd, w0, vi_s, g, g_w0, g_vj, g_vi_s, BN, c);
+    return check_launch("spnb_pbf_viscosity_backward") ? 1 : 0;
 }
 
 }  // extern "C"

@@ -6,6 +6,8 @@ ConvSP layers of one solver iteration, as three differentiable ops with hand-der
 kernels.  ``pbf_stage1/2/3`` return exactly what the torch expressions in their docstrings return
 (same operation order per element).  CUDA float32 tensors only; no fallback.
 """
+import ctypes
+
 import torch
 
 from . import _native as nat
@@ -108,6 +110,100 @@ class _Stage3(torch.autograd.Function):
                 nat.ptr(g_ncount), BN, D, ctx.consts[0], ctx.consts[1], nat.stream()), "spnb_pbf_stage3_backward")
         # d(xnew)/dx = 1 and d/d(cd) = d/d(d0)
         return g, g_d0, g_d0, g_nrm, g_ncount, None, None
+
+
+class _Integrate(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, v, gravity, dt, cap):
+        x, v = _c(x), _c(v)
+        BN, D = x.numel() // x.shape[-1], x.shape[-1]
+        g = (ctypes.c_float * 3)(*([float(t) for t in gravity] + [0.0] * 3)[:3])
+        v2, x1 = torch.empty_like(v), torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            nat.check(nat.lib().spnb_pbf_integrate_forward(nat.ptr(x), nat.ptr(v), nat.ptr(v2), nat.ptr(x1), BN, D,
+                                                           g, dt, cap, nat.stream()), "spnb_pbf_integrate_forward")
+        ctx.save_for_backward(v)
+        ctx.consts = (g, dt, cap)
+        return v2, x1
+
+    @staticmethod
+    def backward(ctx, g_v2, g_x1):
+        v, = ctx.saved_tensors
+        BN, D = v.numel() // v.shape[-1], v.shape[-1]
+        g_v2, g_x1 = _z(g_v2, v), _z(g_x1, v)
+        g_v = torch.empty_like(v)
+        with torch.cuda.device(v.device):
+            nat.check(nat.lib().spnb_pbf_integrate_backward(nat.ptr(v), nat.ptr(g_v2), nat.ptr(g_x1), nat.ptr(g_v), BN,
+                                                            D, ctx.consts[0], ctx.consts[1], ctx.consts[2],
+                                                            nat.stream()), "spnb_pbf_integrate_backward")
+        return g_x1, g_v, None, None, None
+
+
+class _Velocity(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, xs, dt):
+        x, xs = _c(x), _c(xs)
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            nat.check(nat.lib().spnb_pbf_velocity(nat.ptr(x), nat.ptr(xs), nat.ptr(out), None, x.numel(), dt, 0,
+                                                  nat.stream()), "spnb_pbf_velocity")
+        ctx.dt = dt
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        ga = torch.empty_like(g)
+        gb = torch.empty_like(g) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(g.device):
+            nat.check(nat.lib().spnb_pbf_velocity(nat.ptr(g), None, nat.ptr(ga), nat.ptr(gb), g.numel(), ctx.dt, 1,
+                                                  nat.stream()), "spnb_pbf_velocity")
+        return ga, gb, None
+
+
+class _Viscosity(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, w0, vj, vi_s, c):
+        w0, vj, vi_s = _c(w0), _c(vj), _c(vi_s)
+        BN, D = w0.numel() // w0.shape[-1], w0.shape[-1]
+        w1 = torch.empty_like(w0)
+        with torch.cuda.device(w0.device):
+            nat.check(nat.lib().spnb_pbf_viscosity_forward(nat.ptr(w0), nat.ptr(vj), nat.ptr(vi_s), nat.ptr(w1), BN, D,
+                                                           c, nat.stream()), "spnb_pbf_viscosity_forward")
+        ctx.save_for_backward(w0, vi_s)
+        ctx.c = c
+        return w1
+
+    @staticmethod
+    def backward(ctx, g):
+        w0, vi_s = ctx.saved_tensors
+        BN, D = w0.numel() // w0.shape[-1], w0.shape[-1]
+        g = g.contiguous()
+        g_w0, g_vj, g_vi_s = torch.empty_like(w0), torch.empty_like(w0), torch.empty_like(vi_s)
+        with torch.cuda.device(w0.device):
+            nat.check(nat.lib().spnb_pbf_viscosity_backward(nat.ptr(w0), nat.ptr(vi_s), nat.ptr(g), nat.ptr(g_w0),
+                                                            nat.ptr(g_vj), nat.ptr(g_vi_s), BN, D, ctx.c,
+                                                            nat.stream()), "spnb_pbf_viscosity_backward")
+        return g_w0, g_vj, g_vi_s, None
+
+
+def pbf_integrate(x, v, gravity, dt, max_speed):
+    """v1 = v + gravity * dt;  v2 = v1 * -(relu(-max_speed / (|v1| + 1e-4) + 1) - 1)  (fluid_sim.py:240-245);
+    returns (v2, x + v2 * dt)."""
+    return _Integrate.apply(x, v, tuple(float(t) for t in gravity), float(dt), float(max_speed))
+
+
+def pbf_velocity(x, xs, dt):
+    """(x - xs) / dt."""
+    return _Velocity.apply(x, xs, float(dt))
+
+
+def pbf_viscosity(w0, vj, vi_s, c):
+    """w0 + c * (vj - w0 * vi_s)."""
+    return _Viscosity.apply(w0, vj, vi_s, float(c))
 
 
 def pbf_stage1(x, density, nj, ni_s, stiffness, rest_density):

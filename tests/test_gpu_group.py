@@ -211,3 +211,45 @@ def test_pbf_stages_match_torch_expressions(spn):
         close(a, b, "pbf output %d" % i)
     for i, (a, b) in enumerate(zip(res[True][1], res[False][1])):
         close(a, b, "pbf input gradient %d" % i, k=16)
+
+
+def test_pbf_step_ends_match_torch_expressions(spn):
+    """pbf_integrate / pbf_velocity / pbf_viscosity against the torch expressions of fluid_sim.py:355-365 and
+    412-424 (forward and input gradients); speeds straddle the cap so both branches of the clamp are hit."""
+    B, N, D = 2, 1500, 3
+    dt, cap, c = 1.0 / 60, 3.0, 0.37
+    grav = [0.0, -9.8, 0.0]
+    relu = torch.nn.functional.relu
+
+    def run(fused):
+        g = torch.Generator(device="cuda").manual_seed(11)
+        rnd = lambda *s: torch.rand(*s, device="cuda", generator=g)
+        x, xs, vj = (rnd(B, N, D).requires_grad_(True) for _ in range(3))
+        v = ((rnd(B, N, D) - 0.5) * 8.0).requires_grad_(True)
+        vi_s = rnd(B, N, 1).requires_grad_(True)
+        ins = [x, v, xs, vj, vi_s]
+        if fused:
+            v2, x1 = spn.pbf_integrate(x, v, grav, dt, cap)
+            w0 = spn.pbf_velocity(x1, xs, dt)
+            w1 = spn.pbf_viscosity(w0, vj, vi_s, c)
+        else:
+            gt = torch.tensor(grav, device="cuda").view(1, 1, -1)
+            v1 = v + gt * dt
+            vv = torch.norm(v1, 2, v1.dim() - 1, keepdim=True)
+            vv = cap / (vv + 0.0001)
+            vv = -(relu(-vv + 1.0) - 1.0)
+            v2 = v1 * vv
+            x1 = x + v2 * dt
+            w0 = (x1 - xs) / dt
+            w1 = w0 + c * (vj - w0 * vi_s)
+        outs = [v2, x1, w0, w1]
+        gg = torch.Generator(device="cuda").manual_seed(13)
+        gos = [torch.rand(o.shape, device="cuda", generator=gg) for o in outs]
+        torch.autograd.backward(outs, gos)
+        return [o.detach() for o in outs], [i.grad for i in ins]
+
+    a, b = run(True), run(False)
+    for i, (p, q) in enumerate(zip(a[0], b[0])):
+        close(p, q, "output %d" % i)
+    for i, (p, q) in enumerate(zip(a[1], b[1])):
+        close(p, q, "input gradient %d" % i, k=64)
