@@ -164,7 +164,7 @@ def time_kernels(torch, spn, model, locs, vel, iters=10):
         sl, sv, idxs, nb = model.coll(locs, vel)
     nbar = float((nb >= 0).sum().item()) / (B * N)
     flag = nb._spnb_sym_flag
-    tiles = getattr(nb, "_spnb_tiles", None)
+    tiles = spn.tile_lists_of(nb)
     ones = torch.ones(B, N, 1, device="cuda")
     go1, go3 = torch.rand(B, N, 1, device="cuda"), torch.rand(B, N, 3, device="cuda")
     def ev_time(fn):

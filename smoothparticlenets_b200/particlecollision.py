@@ -79,6 +79,19 @@ class _ReorderDataFunction(torch.autograd.Function):
         return None, glocs, gdata, None
 
 
+def tile_lists_of(neighbors):
+    """The compact tile lists (csrc/tile_lists.cuh) of a neighbour tensor returned by ParticleCollision, or
+    None.  Builds them on first use when the module is in its default "lazy" mode."""
+    tiles = getattr(neighbors, "_spnb_tiles", None)
+    if tiles is None:
+        builder = getattr(neighbors, "_spnb_tile_builder", None)
+        if builder is not None:
+            tiles = builder(neighbors)
+            neighbors._spnb_tiles = tiles
+            neighbors._spnb_tile_builder = None
+    return tiles
+
+
 class ParticleCollision(torch.nn.Module):
     """Hash-grid neighbour search (reference ParticleCollision.py:61-203)."""
 
@@ -93,9 +106,13 @@ class ParticleCollision(torch.nn.Module):
         self.max_collisions = ec.check_conditions(max_collisions, "max_collisions", "%s > 0",
                                                   "isinstance(%s, numbers.Integral)")
         self.include_self = 1 if include_self else 0
-        # extension (not in the reference): also emit the compact tile lists that ConvSPGroup consumes;
-        # the float neighbour tensor that is returned is unaffected
-        self.tile_lists = os.environ.get("SPNB_TILE_LISTS", "1") != "0"
+        # extension (not in the reference): the compact tile lists that ConvSPGroup consumes.  "lazy"
+        # (default): built the first time a consumer asks for them (tile_lists_of), so callers that only
+        # use per-layer ConvSP never pay for them; True: built with the lists; False: never.  The float
+        # neighbour tensor that is returned is unaffected.
+        env = os.environ.get("SPNB_TILE_LISTS", "lazy")
+        self.tile_lists = {"0": False, "1": True}.get(env, "lazy")
+        self._generation = 0
         self.radixsort_buffer_size = -1
         # Same buffer names as the reference (ParticleCollision.py:97-100) so state_dicts load.
         # cellStarts/cellEnds are allocated lazily at [B, max_grid_dim**ndim] on first use.
@@ -192,22 +209,34 @@ class ParticleCollision(torch.nn.Module):
                 batch_size, M, N, D, self.max_collisions, ncells, float(self.radius),
                 float(self.radius), self.include_self, nat.ptr(trunc), nat.stream()),
                 "spnb_compute_collisions")
-            tiles = None
+            tiles, builder = None, None
             tile_bytes = (L.spnb_tile_lists_bytes(batch_size, N, D, self.max_collisions)
                           if qlocs is None and self.tile_lists else 0)
             if tile_bytes > 0:
-                # compact sidecar of the same lists (csrc/tile_lists.cuh) for the ConvSPGroup kernels
-                tiles = torch.empty(tile_bytes, device=dev, dtype=torch.uint8)
-                nat.check(L.spnb_build_tile_lists(
-                    nat.ptr(cellIDs), nat.ptr(grid_dims), nat.ptr(cellStarts), nat.ptr(cellEnds),
-                    nat.ptr(neighbors), batch_size, N, D,
-                    self.max_collisions, ncells, nat.ptr(tiles), tile_bytes, nat.stream()),
-                    "spnb_build_tile_lists")
+                self._generation += 1
+                gen, K = self._generation, self.max_collisions
+
+                def builder(nbrs):
+                    """Compact sidecar of `nbrs` (csrc/tile_lists.cuh).  It is derived from this module's
+                    scratch (sorted keys, cell table), so it can only be built until the next forward()."""
+                    if self._generation != gen or tuple(nbrs.shape) != (batch_size, N, K):
+                        return None
+                    with torch.no_grad(), torch.cuda.device(dev):
+                        t = torch.empty(tile_bytes, device=dev, dtype=torch.uint8)
+                        nat.check(L.spnb_build_tile_lists(
+                            nat.ptr(cellIDs), nat.ptr(grid_dims), nat.ptr(cellStarts), nat.ptr(cellEnds),
+                            nat.ptr(nbrs), batch_size, N, D, K, ncells, nat.ptr(t), tile_bytes, nat.stream()),
+                            "spnb_build_tile_lists")
+                    return t
+
+                if self.tile_lists is True:
+                    tiles, builder = builder(neighbors), None
         if qlocs is None:
             # Lists built with the particles as their own queries are symmetric unless one was cut
             # at max_collisions; ConvSP's backward uses this to avoid atomics.
             neighbors._spnb_sym_flag = trunc
             neighbors._spnb_tiles = tiles
+            neighbors._spnb_tile_builder = builder
         self.last_lower_bounds = lower_bounds
         self.last_grid_dims = grid_dims
         if has_data:

@@ -34,10 +34,10 @@ def test_group_matches_per_layer(spn, D, mode):
     r = cases.rng(3)
     locs, vel, L = cases.fluid_cloud(5, B, N, D=D, density=7640.0 if D == 3 else 600.0)
     coll = spn.ParticleCollision(D, 0.1, include_self=False).cuda()
-    coll.tile_lists = mode == "tile"  # tile: compact tile lists; sym/atomic: walk of the float lists
+    coll.tile_lists = "lazy" if mode == "tile" else False  # tile: compact tile lists; sym/atomic: walk of the float lists
     sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
     if mode == "tile":
-        assert int(nb._spnb_tiles[:4].view(torch.int32).item()) == 0, "tile lists usable"
+        assert int(spn.tile_lists_of(nb)[:4].view(torch.int32).item()) == 0, "tile lists usable"
     if mode == "atomic":
         nb = nb.clone()  # drops the symmetry tag -> scatter path
     ones = torch.ones(B, N, 1, device="cuda")
@@ -125,7 +125,7 @@ def test_group_tile_flag_falls_back_on_device(spn):
         coll.tile_lists = tiles_on
         sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
         if tiles_on:
-            assert int(nb._spnb_tiles[:4].view(torch.int32).item()) != 0
+            assert int(spn.tile_lists_of(nb)[:4].view(torch.int32).item()) != 0
         l = sl.detach().clone().requires_grad_(True)
         ones = torch.ones(B, N, 1, device="cuda")
         outs = group(l, [sv, ones], nb)
@@ -154,7 +154,7 @@ def test_group_oversized_tiles_gather_from_global(spn):
         sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
         assert int(nb._spnb_sym_flag.item()) == 0
         if tiles_on:
-            flag, counts, dec, max_total = tl.decode(nb._spnb_tiles, B, N, K)
+            flag, counts, dec, max_total = tl.decode(spn.tile_lists_of(nb), B, N, K)
             assert flag == 0 and max_total + 1 > tl.TILE_CAP
         l = sl.detach().clone().requires_grad_(True)
         ones = torch.ones(B, N, 1, device="cuda")

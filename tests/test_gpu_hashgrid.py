@@ -194,7 +194,7 @@ def test_tile_lists_describe_the_same_lists(spn, B, N, D, extent, radius, K, inc
     G = 16 if extent > 2.0 and D == 3 else 96
     coll = spn.ParticleCollision(D, radius, max_grid_dim=G, max_collisions=K, include_self=bool(include_self)).cuda()
     sl, idxs, nb = coll(gu.dev(locs))
-    tiles = nb._spnb_tiles
+    tiles = spn.tile_lists_of(nb)
     assert tiles is not None and tiles.dtype == torch.uint8
     flag, counts, dec, max_total = tl.decode(tiles, B, N, K)
     nbh = gu.host(nb).astype(np.int64)
@@ -219,7 +219,7 @@ def test_tile_lists_full_size(spn):
     locs, vel, L = cases.fluid_cloud(0, B, N)
     coll = spn.ParticleCollision(3, R, max_collisions=K, include_self=False).cuda()
     sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
-    tiles = nb._spnb_tiles
+    tiles = spn.tile_lists_of(nb)
     assert int(tiles[:4].view(torch.int32).item()) == 0
     lay = tl.layout(B, N, K)
     raw = tiles.cpu().numpy()
@@ -240,3 +240,19 @@ def test_tile_lists_full_size(spn):
     one[l1["list_off"]:] = raw[s0:s0 + nt * tl.TILE_Q * K * 2]
     flag, c1, dec, _ = tl.decode(one, 1, Ns, K)
     assert np.array_equal(dec[0], gu.host(nb[b, :Ns]).astype(np.int64))
+
+
+def test_lazy_tile_lists_are_not_built_from_stale_scratch(spn):
+    """Default mode: the sidecar is built on first request from the module's scratch (sorted keys, cell table);
+    once the module has run again that scratch describes another call, so the request must be refused."""
+    B, N = 2, 500
+    a, _, _ = cases.collision_case(21, B=B, N=N, M=1, D=3, C=1)
+    b, _, _ = cases.collision_case(22, B=B, N=N, M=1, D=3, C=1)
+    coll = spn.ParticleCollision(3, 0.1).cuda()
+    assert coll.tile_lists == "lazy"
+    _, _, nb1 = coll(gu.dev(a))
+    assert getattr(nb1, "_spnb_tiles", None) is None, "nothing is built until somebody asks"
+    _, _, nb2 = coll(gu.dev(b))
+    assert spn.tile_lists_of(nb1) is None
+    t2 = spn.tile_lists_of(nb2)
+    assert t2 is not None and spn.tile_lists_of(nb2) is t2, "built once, cached on the tensor"

@@ -130,7 +130,7 @@ def main():
     }
     # the group ops called directly through the C ABI (pack + tile kernel + fallback), no autograd around them
     from smoothparticlenets_b200 import convsp_group as cg
-    tiles = getattr(nb, "_spnb_tiles", None)
+    tiles = spn.tile_lists_of(nb)
     if os.environ.get("SPNB_MB_NOTILES"):
         tiles = None
 
