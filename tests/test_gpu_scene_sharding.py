@@ -35,19 +35,25 @@ def _worker(rank, world, port, ret):
     d_full = sv.detach().clone().requires_grad_(True)
     out_full = conv(sl, d_full, nb)
     out_full.backward(go_full)
-    # sharded
-    scene = ShardedScene(coll)
-    sl2, idxs2, nb2 = scene.collide(locs)
-    assert torch.equal(sl2, sl) and torch.equal(idxs2, idxs)
-    assert torch.equal(nb2, nb[:, scene.start:scene.end])
-    d_loc = scene.local_rows(sv).detach().clone().requires_grad_(True)
-    out_loc = scene.convsp(conv, d_loc)
-    out_loc.backward(scene.local_rows(go_full).contiguous())
-    ok_out = torch.allclose(out_loc, out_full[:, scene.start:scene.end], rtol=1e-5,
-                            atol=1e-6 * float(out_full.abs().max()))
-    want = d_full.grad[:, scene.start:scene.end]
-    ok_grad = torch.allclose(d_loc.grad, want, rtol=1e-5, atol=4e-6 * float(want.abs().max()))
-    ret[rank] = (bool(ok_out), bool(ok_grad), scene.start, scene.end)
+    # sharded: halo exchange (default) and the all-gather reference
+    oks = []
+    for exchange in ("halo", "allgather"):
+        scene = ShardedScene(coll, exchange=exchange)
+        sl2, idxs2, nb2 = scene.collide(locs)
+        assert torch.equal(sl2, sl) and torch.equal(idxs2, idxs)
+        assert torch.equal(nb2, nb[:, scene.start:scene.end])
+        if exchange == "halo":
+            # the neighbours of a slab of the cell-sorted order are a thin band around it
+            assert 0 < scene.plan.halo_rows() < N // 4, scene.plan.recvs
+        d_loc = scene.local_rows(sv).detach().clone().requires_grad_(True)
+        out_loc = scene.convsp(conv, d_loc)
+        out_loc.backward(scene.local_rows(go_full).contiguous())
+        ok_out = torch.allclose(out_loc, out_full[:, scene.start:scene.end], rtol=1e-5,
+                                atol=1e-6 * float(out_full.abs().max()))
+        want = d_full.grad[:, scene.start:scene.end]
+        ok_grad = torch.allclose(d_loc.grad, want, rtol=1e-5, atol=4e-6 * float(want.abs().max()))
+        oks += [bool(ok_out), bool(ok_grad)]
+    ret[rank] = (all(oks[0::2]), all(oks[1::2]), scene.start, scene.end)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -84,3 +84,57 @@ def test_two_ranks_match_single_process():
         np.testing.assert_allclose(dw, conv.weight.grad.numpy(), rtol=2e-5, atol=1e-6 * np.abs(dw).max())
         np.testing.assert_allclose(db, conv.bias.grad.numpy(), rtol=2e-5)
     assert np.array_equal(res[0][3], res[1][3])
+
+
+def _halo_rows_of(rank, world, N, K, reach):
+    """Synthetic banded neighbour rows of the particles owned by `rank`: indices within +-reach."""
+    from smoothparticlenets_b200 import scene_parallel as sp
+    start, end = sp.owned_range(N, world, rank)
+    nb = -torch.ones(1, end - start, K)
+    for i in range(start, end):
+        js = [j for j in range(i - reach, i + reach + 1, 2) if 0 <= j < N][:K]
+        nb[0, i - start, :len(js)] = torch.tensor(js, dtype=torch.float32)
+    return nb, start, end
+
+
+def _halo_worker(rank, world, port, ret):
+    """One scene over `world` ranks on CPU: the halo exchange (scene_parallel._HaloRows) must hand every rank
+    the rows its lists reference and return to every owner the gradient contributions of ALL ranks -- checked
+    against a single-process computation of the same thing (no collectives)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from smoothparticlenets_b200 import scene_parallel as sp
+    N, C, K, reach = 101, 3, 8, 7
+    g = torch.Generator().manual_seed(5)
+    data = torch.rand(1, N, C, generator=g)
+    nb, start, end = _halo_rows_of(rank, world, N, K, reach)
+    plan = sp.make_halo_plan(nb, N, start, end)
+    assert 0 < plan.halo_rows() <= 2 * reach, (plan.recvs, plan.sends)
+    layer = lambda full, rows, q: (full[0, rows[rows >= 0].long()] * (q + 1.5)).pow(2).sum()
+    x = data[:, start:end].clone().requires_grad_(True)
+    full = sp._HaloRows.apply(x, plan)
+    used = nb[nb >= 0].long()
+    got_rows = full[0, used].detach().clone()
+    layer(full, nb, rank).backward()
+    # reference: the whole scene in this process, the losses of all ranks summed
+    ref = data.clone().requires_grad_(True)
+    sum(layer(ref, _halo_rows_of(q, world, N, K, reach)[0], q) for q in range(world)).backward()
+    ret[rank] = (bool(torch.equal(got_rows, data[0, used])),
+                 bool(torch.allclose(x.grad, ref.grad[:, start:end], rtol=1e-6, atol=1e-6)),
+                 plan.halo_rows())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_matches_single_process_on_three_ranks():
+    world = 3
+    port = 31500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_halo_worker, args=(world, port, ret), nprocs=world, join=True)
+        res = dict(ret)
+    for rank in range(world):
+        same_rows, same_grads, halo = res[rank]
+        assert same_rows and same_grads, (rank, res[rank])

@@ -3,7 +3,7 @@
     python -m torch.distributed.run --nproc-per-node N tools/scene_shard_bench.py [--particles 16777216]
 
 Prints, per step of {sharded ParticleCollision, ConvSP 1->1 and 3->3 forward+backward on the owned
-slice incl. the NCCL all-gather / reduce-scatter of the features}, the max-over-ranks device time."""
+slice incl. the NCCL halo exchange (or all-gather / reduce-scatter) of the features}, the max-over-ranks device time."""
 import argparse
 import os
 import sys
@@ -24,6 +24,7 @@ from smoothparticlenets_b200.scene_parallel import ShardedScene  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--particles", type=int, default=1 << 24)
+    ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"])
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -35,7 +36,7 @@ def main():
     locs = torch.from_numpy((r.rand(1, N, D) * L).astype(np.float32)).cuda()
     vel = torch.from_numpy(r.rand(1, N, D).astype(np.float32)).cuda()
     coll = spn.ParticleCollision(D, 0.1, max_grid_dim=160, include_self=False).cuda()
-    scene = ShardedScene(coll)
+    scene = ShardedScene(coll, exchange=args.exchange)
 
     def timed(fn, iters=3):
         fn()
@@ -70,8 +71,10 @@ def main():
             torch.autograd.grad(out, [d_loc], go)
         layers[name] = timed(fb)
     if rank == 0:
-        print("c5 sharded scene: N=%d over %d GPU(s): ParticleCollision (own rows) %.2f ms; %s" % (
-            N, world, t_coll, "; ".join("ConvSP %s fwd+bwd %.2f ms" % kv for kv in layers.items())))
+        halo = scene.plan.halo_rows() if scene.plan is not None else None
+        print("c5 sharded scene (%s%s): N=%d over %d GPU(s): ParticleCollision (own rows) %.2f ms; %s" % (
+            args.exchange, "" if halo is None else ", %d halo rows on rank 0" % halo, N, world, t_coll,
+            "; ".join("ConvSP %s fwd+bwd %.2f ms" % kv for kv in layers.items())))
     dist.destroy_process_group()
 
 
