@@ -68,8 +68,21 @@ def _compile(src, flags, verbose):
 
 
 def build_library(force=False, verbose=False, extra_flags=()):
-    flags = NVCC_FLAGS + list(extra_flags) + os.environ.get("SPNB_NVCC_EXTRA", "").split()
+    """Compile what changed and (re)link.  Safe to call from several processes at once (one rank per GPU all
+    call it at start-up): an exclusive file lock serialises them, and the up-to-date check does not depend
+    on where the repository is mounted (the GPU box runs a copy under another path)."""
+    import fcntl
     os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose, extra_flags)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose, extra_flags):
+    flags = NVCC_FLAGS + list(extra_flags) + os.environ.get("SPNB_NVCC_EXTRA", "").split()
     if force:
         for old in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, old))
@@ -77,7 +90,7 @@ def build_library(force=False, verbose=False, extra_flags=()):
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as ex:
         objs = list(ex.map(lambda s: _compile(s, flags, verbose), srcs))
     stamp = os.path.join(OBJ, "link.stamp")
-    key = " ".join(objs)
+    key = " ".join(os.path.basename(o) for o in objs)  # content digests, independent of the checkout path
     if force or not os.path.exists(LIB_PATH) or not os.path.exists(stamp) or open(stamp).read() != key:
         cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB_PATH]
         if verbose:
