@@ -59,7 +59,6 @@ constexpr int kThreads = 128;
 #define SPNB_TILE_BWD_G 4
 #endif
 constexpr int kMaxLayers = 6;
-constexpr int kFallbackGrid = 148 * 4;  // blocks of the strided list-walk fallback of a tiled call
 constexpr unsigned kSrcLocs = 15;  // "data is the position tensor"
 
 // ---- compile-time group signature -------------------------------------------------------------------
@@ -269,13 +268,13 @@ __device__ __forceinline__ void layer_scales(const GA& ga, const SphF& sp, float
 #ifndef SPNB_GROUP_FWD_MINB
 #define SPNB_GROUP_FWD_MINB 1
 #endif
-template <typename SG>
+template <typename SG, int THREADS>
 __device__ __forceinline__ void group_fwd_block(const float* __restrict__ rec, const float* __restrict__ neighbors,
-                                                const GroupArgs& ga, int N, int K, int bx, int b, int nbx, int nby)
+                                                const GroupArgs& ga, int N, int K, int bx, int b, int nbx, int nby,
+                                                WalkSmem<SPNB_GROUP_FWD_G>* s_walk)  // one per warp of the block
 {
     constexpr int D = SG::D, V = SG::fwd_vec(), CT = SG::ctot();
-    constexpr int G = SPNB_GROUP_FWD_G, kU = SPNB_GROUP_FWD_U, QPB = kThreads / G, R = 32 / G;
-    __shared__ WalkSmem<G> s_walk[kThreads / 32];
+    constexpr int G = SPNB_GROUP_FWD_G, kU = SPNB_GROUP_FWD_U, QPB = THREADS / G, R = 32 / G;
     const int warp = threadIdx.x >> 5, sub = threadIdx.x % G;
     const int m = bx * QPB + threadIdx.x / G;
     const bool active = m < N;
@@ -361,25 +360,14 @@ __device__ __forceinline__ void group_fwd_block(const float* __restrict__ rec, c
     }
 }
 
-// The list walk as a kernel of its own (no tile lists), and as the device-side FALLBACK of a call that
-// has tile lists: a small grid that returns at once when the tile flag is clear (the tile kernel has
-// done the work) and otherwise strides over the blocks.
+// The list walk as a kernel of its own (calls without tile lists).  With tile lists the same body is the
+// device-side fallback inside the tile kernels (k_tile_fwd / k_tile_bwd), taken when the tile flag is set.
 template <typename SG>
 __global__ void __launch_bounds__(kThreads, SPNB_GROUP_FWD_MINB)
 k_group_fwd(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N, int K)
 {
-    group_fwd_block<SG>(rec, neighbors, ga, N, K, blockIdx.x, blockIdx.y, gridDim.x, gridDim.y);
-}
-template <typename SG>
-__global__ void __launch_bounds__(kThreads, SPNB_GROUP_FWD_MINB)
-k_group_fwd_fallback(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N, int K,
-                     int nbx, int B, const int* __restrict__ tile_flag)
-{
-    if (*tile_flag == 0) return;
-    for (int t = blockIdx.x; t < nbx * B; t += gridDim.x) {
-        group_fwd_block<SG>(rec, neighbors, ga, N, K, t % nbx, t / nbx, nbx, B);
-        __syncthreads();
-    }
+    __shared__ WalkSmem<SPNB_GROUP_FWD_G> s_walk[kThreads / 32];
+    group_fwd_block<SG, kThreads>(rec, neighbors, ga, N, K, blockIdx.x, blockIdx.y, gridDim.x, gridDim.y, s_walk);
 }
 
 // ---- backward ---------------------------------------------------------------------------------------
@@ -388,14 +376,14 @@ k_group_fwd_fallback(const float* __restrict__ rec, const float* __restrict__ ne
 #ifndef SPNB_GROUP_BWD_MINB
 #define SPNB_GROUP_BWD_MINB 1
 #endif
-template <typename SG>
+template <typename SG, int THREADS>
 __device__ __forceinline__ void group_bwd_block(const float* __restrict__ rec, const float* __restrict__ neighbors,
                                                 const GroupArgs& ga, int N, int K, float* dlocs, const int* sym_flag,
-                                                int bx, int b, int nbx, int nby)
+                                                int bx, int b, int nbx, int nby,
+                                                WalkSmem<SPNB_GROUP_BWD_G>* s_walk)  // one per warp of the block
 {
     constexpr int D = SG::D, V = SG::bwd_vec(), CT = SG::ctot();
-    constexpr int G = SPNB_GROUP_BWD_G, UB = SPNB_GROUP_BWD_U, QPB = kThreads / G, R = 32 / G;
-    __shared__ WalkSmem<G> s_walk[kThreads / 32];
+    constexpr int G = SPNB_GROUP_BWD_G, UB = SPNB_GROUP_BWD_U, QPB = THREADS / G, R = 32 / G;
     const bool sym = sym_flag != nullptr && *sym_flag == 0;
     const int warp = threadIdx.x >> 5, sub = threadIdx.x % G;
     const int m = bx * QPB + threadIdx.x / G;
@@ -513,18 +501,9 @@ __global__ void __launch_bounds__(kThreads, SPNB_GROUP_BWD_MINB)
 k_group_bwd(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N, int K,
             float* dlocs, const int* sym_flag)
 {
-    group_bwd_block<SG>(rec, neighbors, ga, N, K, dlocs, sym_flag, blockIdx.x, blockIdx.y, gridDim.x, gridDim.y);
-}
-template <typename SG>
-__global__ void __launch_bounds__(kThreads, SPNB_GROUP_BWD_MINB)
-k_group_bwd_fallback(const float* __restrict__ rec, const float* __restrict__ neighbors, GroupArgs ga, int N, int K,
-                     float* dlocs, const int* sym_flag, int nbx, int B, const int* __restrict__ tile_flag)
-{
-    if (*tile_flag == 0) return;
-    for (int t = blockIdx.x; t < nbx * B; t += gridDim.x) {
-        group_bwd_block<SG>(rec, neighbors, ga, N, K, dlocs, sym_flag, t % nbx, t / nbx, nbx, B);
-        __syncthreads();
-    }
+    __shared__ WalkSmem<SPNB_GROUP_BWD_G> s_walk[kThreads / 32];
+    group_bwd_block<SG, kThreads>(rec, neighbors, ga, N, K, dlocs, sym_flag, blockIdx.x, blockIdx.y, gridDim.x,
+                                  gridDim.y, s_walk);
 }
 
 // ---- tile-list kernels --------------------------------------------------------------------------------
@@ -645,7 +624,8 @@ __device__ __forceinline__ void tile_walk(const unsigned char* __restrict__ my_u
 
 template <typename SG, int G>
 __global__ void __launch_bounds__(kTileQ * G)
-k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int K, long long BN)
+k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int K, long long BN,
+           const float* __restrict__ neighbors)
 {
     constexpr int D = SG::D, V = SG::fwd_vec(), CT = SG::ctot();
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -657,7 +637,18 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     // predecessors only), so the flag test does not add a global-memory latency to the prologue
     int desc_word = 0;
     if (tid < 32) desc_word = __ldg(reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb) + tid);
-    if (*ta.flag != 0) return;
+    if (*ta.flag != 0) {
+        // tile lists unusable for this call (a list reached K, ...): the float-list walk, strided over the
+        // grid, with the (unused) tile buffer as its row-staging scratch; records are record-major then
+        constexpr int THREADS = kTileQ * G;
+        const int nbx = (int)(((long long)N * SPNB_GROUP_FWD_G + THREADS - 1) / THREADS), B = gridDim.y;
+        for (int t = blockIdx.y * gridDim.x + blockIdx.x; t < nbx * B; t += gridDim.x * gridDim.y) {
+            group_fwd_block<SG, THREADS>(rec, neighbors, ga, N, K, t % nbx, t / nbx, nbx, B,
+                                         reinterpret_cast<WalkSmem<SPNB_GROUP_FWD_G>*>(s_raw));
+            __syncthreads();
+        }
+        return;
+    }
     if (tid < 32) reinterpret_cast<int*>(&s_desc)[tid] = desc_word;
     if (tid == 0) mbar_init(&s_bar, 1);
     if (tid < V) s_rec[tid * kTileCap] = tid == 0 ? make_float4(1e18f, 1e18f, 1e18f, 0.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -752,9 +743,12 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     }
 }
 
+// (min blocks: the staged tile bounds the residency at 3 CTAs per SM for four-plane records and 4 for
+//  three-plane ones; keep the registers of the merged tile + list-walk code within that)
 template <typename SG, int G>
-__global__ void __launch_bounds__(kTileQ * G)
-k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int K, long long BN, float* dlocs)
+__global__ void __launch_bounds__(kTileQ * G, (kTileQ * G >= 256 ? (SG::bwd_vec() <= 3 ? 4 : 3) : 1))
+k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int K, long long BN, float* dlocs,
+           const float* __restrict__ neighbors, const int* sym_flag)
 {
     constexpr int D = SG::D, V = SG::bwd_vec(), CT = SG::ctot();
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -766,7 +760,17 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     // predecessors only), so the flag test does not add a global-memory latency to the prologue
     int desc_word = 0;
     if (tid < 32) desc_word = __ldg(reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb) + tid);
-    if (*ta.flag != 0) return;
+    if (*ta.flag != 0) {
+        // tile lists unusable for this call: the float-list walk (gather or atomics mode by sym_flag)
+        constexpr int THREADS = kTileQ * G;
+        const int nbx = (int)(((long long)N * SPNB_GROUP_BWD_G + THREADS - 1) / THREADS), B = gridDim.y;
+        for (int t = blockIdx.y * gridDim.x + blockIdx.x; t < nbx * B; t += gridDim.x * gridDim.y) {
+            group_bwd_block<SG, THREADS>(rec, neighbors, ga, N, K, dlocs, sym_flag, t % nbx, t / nbx, nbx, B,
+                                         reinterpret_cast<WalkSmem<SPNB_GROUP_BWD_G>*>(s_raw));
+            __syncthreads();
+        }
+        return;
+    }
     if (tid < 32) reinterpret_cast<int*>(&s_desc)[tid] = desc_word;
     if (tid == 0) mbar_init(&s_bar, 1);
     if (tid < V) s_rec[tid * kTileCap] = tid == 0 ? make_float4(1e18f, 1e18f, 1e18f, 0.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -987,8 +991,8 @@ static bool allow_smem(KernelT* kernel, size_t bytes)
     return true;
 }
 
-// With tile lists: pack (layout chosen on the device by the tile flag), the tile kernel (runs when the
-// flag is 0), the list walk (runs when it is not).  Without: pack + list walk.
+// With tile lists: pack (layout chosen on the device by the tile flag) + the tile kernel, which runs the
+// float-list walk itself when the flag is set.  Without: pack + list walk.
 template <typename SG>
 static int run_fwd(const float* locs, const float* neighbors, const GroupArgs& ga, int B, int N, int K,
                    float* rec, const void* tiles, cudaStream_t stream)
@@ -996,22 +1000,19 @@ static int run_fwd(const float* locs, const float* neighbors, const GroupArgs& g
     const long long BN = (long long)B * N;
     TileArgs ta;
     const bool tiled = make_tile_args(tiles, B, N, K, ta);
-    const int* tflag = tiled ? ta.flag : nullptr;
-    k_group_pack<SG, false><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec, tflag, nullptr, nullptr);
+    k_group_pack<SG, false><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec, tiled ? ta.flag : nullptr, nullptr, nullptr);
     if (!launched("k_group_pack")) return -1;
     if (tiled) {
         constexpr int G = SPNB_TILE_FWD_G > 0 ? SPNB_TILE_FWD_G : (SG::fwd_vec() == 1 ? 1 : 2);
+        static_assert(sizeof(WalkSmem<SPNB_GROUP_FWD_G>) * (kTileQ * G / 32) <= kTileCap * sizeof(float4), "walk scratch fits the tile buffer");
         const size_t smem = (size_t)SG::fwd_vec() * kTileCap * sizeof(float4);
         if (!allow_smem(k_tile_fwd<SG, G>, smem)) return -1;
-        k_tile_fwd<SG, G><<<dim3(ta.ntb, B), kTileQ * G, smem, stream>>>(rec, ta, ga, N, K, BN);
+        k_tile_fwd<SG, G><<<dim3(ta.ntb, B), kTileQ * G, smem, stream>>>(rec, ta, ga, N, K, BN, neighbors);
         if (!launched("k_tile_fwd")) return -1;
+    } else {
+        k_group_fwd<SG><<<dim3(cdiv((long long)N * SPNB_GROUP_FWD_G, kThreads), B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K);
     }
-    const int nbx = cdiv((long long)N * SPNB_GROUP_FWD_G, kThreads);
-    if (tiled)
-        k_group_fwd_fallback<SG><<<kFallbackGrid, kThreads, 0, stream>>>(rec, neighbors, ga, N, K, nbx, B, tflag);
-    else
-        k_group_fwd<SG><<<dim3(nbx, B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K);
-    return tiled ? 3 : 2;
+    return 2;
 }
 template <typename SG>
 static int run_bwd(const float* locs, const float* neighbors, const GroupArgs& ga, int B, int N, int K,
@@ -1020,22 +1021,19 @@ static int run_bwd(const float* locs, const float* neighbors, const GroupArgs& g
     const long long BN = (long long)B * N;
     TileArgs ta;
     const bool tiled = make_tile_args(tiles, B, N, K, ta);
-    const int* tflag = tiled ? ta.flag : nullptr;
-    k_group_pack<SG, true><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec, tflag, dlocs, sym_flag);
+    k_group_pack<SG, true><<<cdiv(BN, 256), 256, 0, stream>>>(locs, ga, BN, rec, tiled ? ta.flag : nullptr, dlocs, sym_flag);
     if (!launched("k_group_pack")) return -1;
     if (tiled) {
         constexpr int G = SPNB_TILE_BWD_G;
+        static_assert(sizeof(WalkSmem<SPNB_GROUP_BWD_G>) * (kTileQ * G / 32) <= kTileCap * sizeof(float4), "walk scratch fits the tile buffer");
         const size_t smem = (size_t)SG::bwd_vec() * kTileCap * sizeof(float4);
         if (!allow_smem(k_tile_bwd<SG, G>, smem)) return -1;
-        k_tile_bwd<SG, G><<<dim3(ta.ntb, B), kTileQ * G, smem, stream>>>(rec, ta, ga, N, K, BN, dlocs);
+        k_tile_bwd<SG, G><<<dim3(ta.ntb, B), kTileQ * G, smem, stream>>>(rec, ta, ga, N, K, BN, dlocs, neighbors, sym_flag);
         if (!launched("k_tile_bwd")) return -1;
+    } else {
+        k_group_bwd<SG><<<dim3(cdiv((long long)N * SPNB_GROUP_BWD_G, kThreads), B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K, dlocs, sym_flag);
     }
-    const int nbx = cdiv((long long)N * SPNB_GROUP_BWD_G, kThreads);
-    if (tiled)
-        k_group_bwd_fallback<SG><<<kFallbackGrid, kThreads, 0, stream>>>(rec, neighbors, ga, N, K, dlocs, sym_flag, nbx, B, tflag);
-    else
-        k_group_bwd<SG><<<dim3(nbx, B), kThreads, 0, stream>>>(rec, neighbors, ga, N, K, dlocs, sym_flag);
-    return tiled ? 3 : 2;
+    return 2;
 }
 
 static size_t record_floats(const Signature& sg, bool bwd)

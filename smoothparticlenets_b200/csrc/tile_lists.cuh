@@ -35,8 +35,9 @@
 //
 // flag (first int of the buffer) != 0 marks the sidecar unusable for this call: bit 0 = a list is full,
 // i.e. may have been cut at K (the symmetric backward is then invalid, see convsp_group.cu), bit 1 = a
-// neighbour lies outside the block's ranges or a tile has more than 4095 records.  Consumers test it on the DEVICE and the ordinary list walk runs instead, so nothing
-// depends on a host synchronisation.
+// neighbour lies outside the block's ranges or a tile has more than 4095 records.  Consumers test it on
+// the DEVICE and run the ordinary list walk instead (inside the same kernel), so nothing depends on a
+// host synchronisation.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
