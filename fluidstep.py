@@ -117,15 +117,19 @@ class FluidStep(nn.Module):
         for _ in range(NUM_ITERATIONS if self.pbf is not None else 0):
             # same data flow as below; the elementwise arithmetic between the groups in three fused stages
             pbf = self.pbf
+            # new_locs has 8 consumers per iteration: give each its own alias so that the 8 gradients are
+            # added in one kernel (pbf.fanout) instead of 7 pairwise accumulations
+            fan = pbf.fanout(new_locs, 8) if hasattr(pbf, "fanout") else (new_locs,) * 8
+            xa, xa1, xa2, x1, xb, x2, xc, x3 = fan
             density, nj, ni_s, nj_c, ni_cs, ncount = self.group_a(
-                new_locs, [ones, new_locs, ones, new_locs, ones, ones], neighbors)
-            pressure, xp, nij = pbf.pbf_stage1(new_locs, density, nj, ni_s, self.stiffness, self.density_rest)
-            njp, nip_s = self.group_b(new_locs, [xp, pressure], neighbors)
-            delta0, normals = pbf.pbf_stage2(new_locs, pressure, nij, njp, nip_s, nj_c, ni_cs, COHESION,
+                xa, [ones, xa1, ones, xa2, ones, ones], neighbors)
+            pressure, xp, nij = pbf.pbf_stage1(x1, density, nj, ni_s, self.stiffness, self.density_rest)
+            njp, nip_s = self.group_b(xb, [xp, pressure], neighbors)
+            delta0, normals = pbf.pbf_stage2(x2, pressure, nij, njp, nip_s, nj_c, ni_cs, COHESION,
                                              self.radius, SURFACE_TENSION, self.density_rest,
                                              SURFACE_CONSTRAINT_SCALE)
-            cd, = self.group_c(new_locs, [normals], neighbors)
-            new_locs = pbf.pbf_stage3(new_locs, delta0, cd, normals, ncount, RELAXATION, DAMP)
+            cd, = self.group_c(xc, [normals], neighbors)
+            new_locs = pbf.pbf_stage3(x3, delta0, cd, normals, ncount, RELAXATION, DAMP)
         for _ in range(NUM_ITERATIONS if (self.fused and self.pbf is None) else 0):
             # same data flow as below; layers sharing (new_locs, neighbors) grouped by dependency
             density, nj, ni_s, nj_c, ni_cs, ncount = self.group_a(

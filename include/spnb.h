@@ -199,6 +199,10 @@ int spnb_pbf_stage3_backward(const float* d0, const float* cd, const float* nrm,
                              const float* g, float* g_d0, float* g_nrm, float* g_ncount, long long BN,
                              int ndims, float relaxation, float damp, void* stream);
 
+/* out = inputs[0] + ... + inputs[n-1] (1 <= n <= 8; inputs_host: HOST array of n device pointers): the
+ * backward of a fan-out, one pass instead of autograd's n-1 pairwise adds. */
+int spnb_sum_n(const float* const* inputs_host, int n, float* out, long long nfloats, void* stream);
+
 /* The ends of the step (fluid_sim.py:355-365, 412-424): gravity + velocity cap + position update
  * (gravity: HOST array of ndims floats), velocity from the position change ((a - b) / dt; backward != 0:
  * o = a / dt and, when o2 != NULL, o2 = -(a / dt)), and the XSPH viscosity update w0 + c*(vj - w0*vi_s). */

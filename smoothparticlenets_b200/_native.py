@@ -40,6 +40,7 @@ _SIGNATURES = {
     "spnb_pbf_stage2_backward": (_i, [_vp] * 14 + [ctypes.c_longlong, _i, _f, _f, _f, _f, _f, _vp]),
     "spnb_pbf_stage3_forward": (_i, [_vp] * 6 + [ctypes.c_longlong, _i, _f, _f, _vp]),
     "spnb_pbf_stage3_backward": (_i, [_vp] * 8 + [ctypes.c_longlong, _i, _f, _f, _vp]),
+    "spnb_sum_n": (_i, [ctypes.POINTER(_vp), _i, _vp, ctypes.c_longlong, _vp]),
     "spnb_pbf_integrate_forward": (_i, [_vp] * 4 + [ctypes.c_longlong, _i, ctypes.POINTER(_f), _f, _f, _vp]),
     "spnb_pbf_integrate_backward": (_i, [_vp] * 4 + [ctypes.c_longlong, _i, ctypes.POINTER(_f), _f, _f, _vp]),
     "spnb_pbf_velocity": (_i, [_vp] * 4 + [ctypes.c_longlong, _f, _i, _vp]),

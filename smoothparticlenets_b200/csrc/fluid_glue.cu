@@ -288,6 +288,33 @@ k_pbf_viscosity_bwd(const float* __restrict__ w0, const float* __restrict__ vi_s
     g_vi_s[n] = acc;
 }
 
+// ---- n-ary sum (backward of a fan-out) --------------------------------------------------------------------
+// A tensor with k consumers receives k gradients, which autograd adds pairwise: k-1 launches that each
+// re-read the running sum.  The fan-out op (pbf.py: fanout) hands every consumer its own alias of the tensor
+// and adds all gradients here in one pass.
+struct SumPtrs { const float* p[8]; };
+
+__global__ void __launch_bounds__(kGlueThreads)
+k_sum_n(SumPtrs in, int n, float* __restrict__ out, long long nfloat4, long long nfloats)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nfloat4) {
+        float4 acc = reinterpret_cast<const float4*>(in.p[0])[i];
+        for (int k = 1; k < n; ++k) {
+            const float4 v = reinterpret_cast<const float4*>(in.p[k])[i];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(out)[i] = acc;
+    } else {
+        const long long j = nfloat4 * 4 + (i - nfloat4);  // tail elements
+        if (j < nfloats) {
+            float acc = in.p[0][j];
+            for (int k = 1; k < n; ++k) acc += in.p[k][j];
+            out[j] = acc;
+        }
+    }
+}
+
 }  // namespace
 }  // namespace spnb
 
@@ -391,6 +418,30 @@ int spnb_pbf_stage3_backward(const float* d0, const float* cd, const float* nrm,
     }
     SPNB_GLUE_LAUNCH(k_pbf3_bwd, d0, cd, nrm, ncount, g, g_d0, g_nrm, g_ncount, BN, relaxation, damp);
     return check_launch("spnb_pbf_stage3_backward") ? 1 : 0;
+}
+
+int spnb_sum_n(const float* const* inputs_host, int n, float* out, long long nfloats, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!inputs_host || !out || n < 1 || n > 8 || nfloats <= 0) {
+        set_error("spnb_sum_n: bad arguments (1 <= n <= 8)");
+        return 0;
+    }
+    SumPtrs in;
+    bool aligned = (reinterpret_cast<size_t>(out) & 15) == 0;
+    for (int k = 0; k < 8; ++k) {
+        in.p[k] = k < n ? inputs_host[k] : nullptr;
+        if (k < n && !in.p[k]) {
+            set_error("spnb_sum_n: null input");
+            return 0;
+        }
+        if (k < n && (reinterpret_cast<size_t>(in.p[k]) & 15) != 0) aligned = false;
+    }
+    const long long n4 = aligned ? nfloats / 4 : 0;
+    const long long threads = n4 + (nfloats - n4 * 4);
+    k_sum_n<<<cdiv(threads, kGlueThreads), kGlueThreads, 0, stream>>>(in, n, out, n4, nfloats);
+    count_launches(1);
+    return check_launch("spnb_sum_n") ? 1 : 0;
 }
 
 int spnb_pbf_integrate_forward(const float* x, const float* v, float* v2, float* x1, long long BN, int D,

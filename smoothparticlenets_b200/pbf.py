@@ -190,6 +190,40 @@ class _Viscosity(torch.autograd.Function):
         return g_w0, g_vj, g_vi_s, None
 
 
+class _Fanout(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.n = n
+        return tuple(x.view_as(x) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        gs = [g.contiguous() for g in grads if g is not None]
+        if not gs:
+            return None, None
+        if len(gs) == 1:
+            return gs[0], None
+        out = torch.empty_like(gs[0])
+        with torch.cuda.device(out.device):
+            first = True
+            while gs:
+                # up to 8 inputs per launch; further launches add onto the running sum (element-wise in place)
+                chunk, gs = (gs[:8], gs[8:]) if first else ([out] + gs[:7], gs[7:])
+                first = False
+                ptrs = (ctypes.c_void_p * len(chunk))(*[t.data_ptr() for t in chunk])
+                nat.check(nat.lib().spnb_sum_n(ptrs, len(chunk), nat.ptr(out), out.numel(), nat.stream()),
+                          "spnb_sum_n")
+        return out, None
+
+
+def fanout(x, n):
+    """n aliases of x (views, no copy) for n consumers; the n gradients that come back are added in ONE
+    kernel instead of autograd's n-1 pairwise accumulation launches.  Values are untouched."""
+    nat.require_cuda_f32(x, "fanout operand")
+    return _Fanout.apply(x, int(n))
+
+
 def pbf_integrate(x, v, gravity, dt, max_speed):
     """v1 = v + gravity * dt;  v2 = v1 * -(relu(-max_speed / (|v1| + 1e-4) + 1) - 1)  (fluid_sim.py:240-245);
     returns (v2, x + v2 * dt)."""

@@ -253,3 +253,20 @@ def test_pbf_step_ends_match_torch_expressions(spn):
         close(p, q, "output %d" % i)
     for i, (p, q) in enumerate(zip(a[1], b[1])):
         close(p, q, "input gradient %d" % i, k=64)
+
+
+@pytest.mark.parametrize("n,shape", [(2, (2, 1000, 3)), (8, (1, 777, 3)), (11, (3, 5, 1)), (1, (1, 10, 3))])
+def test_fanout_adds_all_gradients(spn, n, shape):
+    """fanout(x, n): n aliases of x whose gradients come back added in one pass (two launches above 8)."""
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.rand(*shape, device="cuda", generator=g).requires_grad_(True)
+    ws = [torch.rand(*shape, device="cuda", generator=g) for _ in range(n)]
+    n0 = nat.lib().spnb_launch_count()
+    outs = spn.fanout(x, n)
+    assert len(outs) == n and all(torch.equal(o, x) and o.data_ptr() == x.data_ptr() for o in outs)
+    sum((o * w).sum() for o, w in zip(outs, ws)).backward()
+    assert nat.lib().spnb_launch_count() - n0 == (0 if n == 1 else 1 if n <= 8 else 2)
+    want = ws[0].clone()
+    for w in ws[1:]:
+        want = want + w
+    close(x.grad, want, "fanout gradient")
