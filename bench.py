@@ -126,6 +126,11 @@ def run_reference_arm(args):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     n = args.cpu_particles
+    # load the reference's compiled CPU extension (oracle/_ref) in THIS process too: the pool workers are forked
+    # from it, and the driver's record of loaded native libraries then shows what the arm actually ran
+    from oracle import cpu_modules as cm
+    parent_kind = cm.backend().kind
+    _cpu_scene_step((99, 256))
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for w in range(args.warmup):
@@ -163,7 +168,7 @@ def time_kernels(torch, spn, model, locs, vel, iters=10):
     with torch.no_grad():
         sl, sv, idxs, nb = model.coll(locs, vel)
     nbar = float((nb >= 0).sum().item()) / (B * N)
-    flag = nb._spnb_sym_flag
+    flag = spn.sym_flag_of(nb)
     tiles = spn.tile_lists_of(nb)
     ones = torch.ones(B, N, 1, device="cuda")
     go1, go3 = torch.rand(B, N, 1, device="cuda"), torch.rand(B, N, 3, device="cuda")

@@ -16,6 +16,10 @@ from . import spn_oracle as so
 KERNEL_NAMES = so.KERNEL_NAMES
 
 _backend = None
+# False: the reference CPU path's own (unstable) selection sort, cpu_layer_funcs.cpp:263-287 -- what the CPU
+# baseline times.  True: the stable order of the reference's GPU path (and of the product), so that a test can
+# compare the two steps with the SAME permutation and neighbour order (set by tests only; needs the C port).
+STABLE_ORDER = False
 
 
 def backend():
@@ -126,7 +130,10 @@ class ParticleCollision(torch.nn.Module):
         be = backend()
         ln = _np(locs)
         low, gd = so.grid_bounds_torch(ln, self.radius, self.max_grid_dim)  # the reference's torch ops
-        ids, idxs = be.hashgrid_order(ln, low, gd, self.radius, stable=False)  # its selection sort
+        if STABLE_ORDER:
+            ids, idxs = so.COracle().hashgrid_order(ln, low, gd, self.radius, stable=True)
+        else:
+            ids, idxs = be.hashgrid_order(ln, low, gd, self.radius, stable=False)  # its selection sort
         idxs_t = torch.from_numpy(idxs)
         if data is not None:
             locs, data = self.reorder(idxs_t, locs, data)

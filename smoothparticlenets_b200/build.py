@@ -85,11 +85,12 @@ def _build_locked(force, verbose, extra_flags):
     flags = NVCC_FLAGS + list(extra_flags) + os.environ.get("SPNB_NVCC_EXTRA", "").split()
     if force:
         for old in os.listdir(OBJ):
-            os.remove(os.path.join(OBJ, old))
+            if old != "build.lock":  # the lock is held (flock) by this very call
+                os.remove(os.path.join(OBJ, old))
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as ex:
         objs = list(ex.map(lambda s: _compile(s, flags, verbose), srcs))
-    stamp = os.path.join(OBJ, "link.stamp")
+    stamp = os.path.join(OBJ, "link.%s.stamp" % os.path.basename(LIB_PATH))  # one stamp per variant library
     key = " ".join(os.path.basename(o) for o in objs)  # content digests, independent of the checkout path
     if force or not os.path.exists(LIB_PATH) or not os.path.exists(stamp) or open(stamp).read() != key:
         cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", LIB_PATH]

@@ -12,6 +12,7 @@ import torch
 
 from . import _native as nat
 from . import error_checking as ec
+from . import sidecar
 from .kernels import KERNEL_NAMES
 
 
@@ -69,7 +70,8 @@ class ConvSP(torch.nn.Module):
             qlocs = qlocs.contiguous()
         # Symmetry tag left by ParticleCollision on the neighbour tensor it returned (device int32:
         # 0 = every list is complete, so the relation is symmetric).
-        sym_flag = getattr(neighbors, "_spnb_sym_flag", None) if qlocs is None else None
+        sc = sidecar.lookup(neighbors) if qlocs is None else None
+        sym_flag = None if sc is None else sc.sym_flag
         neighbors = neighbors.contiguous() if not neighbors.is_contiguous() else neighbors
         return _ConvSPFunction.apply(qlocs, locs, data, neighbors, self.weight, self.bias,
                                      float(self.radius), self.kernel_size, self.dilation,

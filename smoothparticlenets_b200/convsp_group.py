@@ -18,7 +18,7 @@ import torch
 
 from . import _native as nat
 from .convsp import ConvSP
-from .particlecollision import tile_lists_of
+from .particlecollision import tile_lists_of, sym_flag_of
 
 
 class ConvSPGroup(torch.nn.Module):
@@ -48,7 +48,7 @@ class ConvSPGroup(torch.nn.Module):
         if fused:
             locs_c = locs.contiguous()
             datas_c = [d.contiguous() for d in datas]
-            sym_flag = getattr(neighbors, "_spnb_sym_flag", None)
+            sym_flag = sym_flag_of(neighbors)
             tiles = tile_lists_of(neighbors)
             cfg = tuple((l.kernel_fn, l.dis_norm, l.nchannels, l.nkernels) for l in layers)
             flat = list(datas_c) + [l.weight for l in layers] + [l.bias for l in layers]

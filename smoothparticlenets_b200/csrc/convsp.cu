@@ -108,11 +108,13 @@ k_convsp_fwd_generic(const float* __restrict__ qlocs, const float* __restrict__ 
         float acc[kOChunk];
 #pragma unroll
         for (int o = 0; o < kOChunk; ++o) acc[o] = 0.0f;
+        bool done = !active;  // my group's row has ended (the list stops at its first negative entry)
         for (int jj0 = 0; jj0 < K; jj0 += kG) {
             const int jj = jj0 + sub;
-            const float nb = (active && jj < K) ? row[jj] : -1.0f;
+            const float nb = (!done && jj < K) ? row[jj] : -1.0f;
             const unsigned neg = __ballot_sync(0xffffffffu, !(nb >= 0.0f));
             const int fneg = group_first_neg(neg, lane, sub);
+            if (fneg < kG) done = true;
             if (sub < fneg) {
                 const int j = (int)nb;
                 const float* y = sl + (size_t)j * D;
@@ -158,7 +160,7 @@ k_convsp_fwd_generic(const float* __restrict__ qlocs, const float* __restrict__ 
                     }
                 }
             }
-            if (__all_sync(0xffffffffu, fneg < kG)) break;
+            if (__all_sync(0xffffffffu, done)) break;
         }
 #pragma unroll
         for (int o = 0; o < kOChunk; ++o) acc[o] = group_sum(acc[o]);
@@ -207,11 +209,13 @@ k_convsp_bwd_generic(const float* __restrict__ qlocs, const float* __restrict__ 
 #pragma unroll
     for (int k = 0; k < D; ++k) a_dq[k] = 0.0f;
 
+    bool done = !active;  // my group's row has ended (the list stops at its first negative entry)
     for (int jj0 = 0; jj0 < K; jj0 += kG) {
         const int jj = jj0 + sub;
-        const float nb = (active && jj < K) ? row[jj] : -1.0f;
+        const float nb = (!done && jj < K) ? row[jj] : -1.0f;
         const unsigned neg = __ballot_sync(0xffffffffu, !(nb >= 0.0f));
         const int fneg = group_first_neg(neg, lane, sub);
+        if (fneg < kG) done = true;
         if (sub < fneg) {
             const int j = (int)nb;
             const float* y = sl + (size_t)j * D;
@@ -279,7 +283,7 @@ k_convsp_bwd_generic(const float* __restrict__ qlocs, const float* __restrict__ 
                 }
             }
         }
-        if (__all_sync(0xffffffffu, fneg < kG)) break;
+        if (__all_sync(0xffffffffu, done)) break;
     }
 #pragma unroll
     for (int k = 0; k < D; ++k) a_dq[k] = group_sum(a_dq[k]);
@@ -330,11 +334,13 @@ k_convsp_dweight_generic(const float* __restrict__ qlocs, const float* __restric
     const float* sd = data + (size_t)b * N * C;
     const float* gi = go + qq * O;
 
+    bool done = !active;  // my group's row has ended (the list stops at its first negative entry)
     for (int jj0 = 0; jj0 < K; jj0 += kG) {
         const int jj = jj0 + sub;
-        const float nb = (active && jj < K) ? row[jj] : -1.0f;
+        const float nb = (!done && jj < K) ? row[jj] : -1.0f;
         const unsigned neg = __ballot_sync(0xffffffffu, !(nb >= 0.0f));
         const int fneg = group_first_neg(neg, lane, sub);
+        if (fneg < kG) done = true;
         bool live = sub < fneg;
         const int j = live ? (int)nb : 0;
         const float* dj = sd + (size_t)j * C;
@@ -384,7 +390,7 @@ k_convsp_dweight_generic(const float* __restrict__ qlocs, const float* __restric
                     }
             }
         }
-        if (__all_sync(0xffffffffu, fneg < kG)) break;
+        if (__all_sync(0xffffffffu, done)) break;
     }
     if (acc_in_smem) {
         __syncthreads();

@@ -183,7 +183,7 @@ k_group_pack(const float* __restrict__ locs, GroupArgs ga, long long BN, float* 
              const int* __restrict__ tile_flag, float* __restrict__ dlocs, const int* __restrict__ sym_flag)
 {
     // planar (one float4 array per record quarter) for the tile kernels, record-major for the list walk
-    const bool planar = tile_flag != nullptr && *tile_flag == 0;
+    const bool planar = tile_flag != nullptr && *tile_flag == 0 && !(BWD && sym_flag != nullptr && *sym_flag != 0);
     constexpr int V = BWD ? SG::bwd_vec() : SG::fwd_vec();
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= BN) return;
@@ -760,8 +760,9 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     // predecessors only), so the flag test does not add a global-memory latency to the prologue
     int desc_word = 0;
     if (tid < 32) desc_word = __ldg(reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb) + tid);
-    if (*ta.flag != 0) {
-        // tile lists unusable for this call: the float-list walk (gather or atomics mode by sym_flag)
+    if (*ta.flag != 0 || (sym_flag != nullptr && *sym_flag != 0)) {
+        // tile lists unusable for this call, or the relation is not symmetric (the tile path only has the
+        // gather mode): the float-list walk (gather or atomics mode by sym_flag)
         constexpr int THREADS = kTileQ * G;
         const int nbx = (int)(((long long)N * SPNB_GROUP_BWD_G + THREADS - 1) / THREADS), B = gridDim.y;
         for (int t = blockIdx.y * gridDim.x + blockIdx.x; t < nbx * B; t += gridDim.x * gridDim.y) {

@@ -547,7 +547,7 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
     int total_cells = 1;
 #pragma unroll
     for (int k = 0; k < D; ++k) total_cells *= 3;
-    bool truncated = false;
+    bool truncated = false;  // a row was cut at K, or a query lies beyond the clamped grid: relation not symmetric
 
     int qi = 0;
     while (qi < nq) {
@@ -563,6 +563,12 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
         }
         const unsigned sm = __ballot_sync(0xffffffffu, same);
         const int run = __ffs(~sm) - 1;  // leading ones (lane 0 always matches itself)
+        // A query two or more cells past the upper border of a clamped grid sees no cell at all, while the
+        // border cell it was hashed into (partial_grid_hash clamps, loc2grid does not: common_funcs.h:96-119,
+        // 913-914) is still scanned by its neighbours: the relation is then not symmetric.
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            if (gd[k] > 0.0f && (float)gc[k] >= gd[k] + 1.0f) truncated = true;
         if (lane < run) s_found[warp][lane] = 0;
         __syncwarp();
 

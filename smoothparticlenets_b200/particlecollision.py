@@ -8,11 +8,13 @@ cell table and neighbour lists run without a host synchronisation.
 """
 import numbers  # noqa: F401
 import os
+import weakref
 
 import torch
 
 from . import _native as nat
 from . import error_checking as ec
+from . import sidecar
 from .convsp import nat_max_dim
 
 
@@ -81,15 +83,46 @@ class _ReorderDataFunction(torch.autograd.Function):
 
 def tile_lists_of(neighbors):
     """The compact tile lists (csrc/tile_lists.cuh) of a neighbour tensor returned by ParticleCollision, or
-    None.  Builds them on first use when the module is in its default "lazy" mode."""
-    tiles = getattr(neighbors, "_spnb_tiles", None)
-    if tiles is None:
-        builder = getattr(neighbors, "_spnb_tile_builder", None)
-        if builder is not None:
-            tiles = builder(neighbors)
-            neighbors._spnb_tiles = tiles
-            neighbors._spnb_tile_builder = None
-    return tiles
+    None.  Builds them on first use when the module is in its default "lazy" mode.  None as well when the
+    tensor was edited in place after ParticleCollision returned it (sidecar.py)."""
+    sc = sidecar.lookup(neighbors)
+    if sc is None:
+        return None
+    if sc.tiles is None and sc.builder is not None:
+        sc.tiles = sc.builder(neighbors)
+        sc.builder = None
+    return sc.tiles
+
+
+def sym_flag_of(neighbors):
+    """Device int32[1] left by ParticleCollision (0 = every list is complete and no query lies beyond a clamped
+    grid, so the neighbour relation is symmetric), or None for tensors of unknown origin / edited in place."""
+    sc = sidecar.lookup(neighbors)
+    return None if sc is None else sc.sym_flag
+
+
+class _TileBuilder(object):
+    """Lazy construction of the tile lists from the module's scratch (sorted keys, cell table).  Holds the module
+    weakly and refuses once the module has run again (its scratch then describes another call)."""
+
+    def __init__(self, module, gen, shape, tile_bytes, grid_dims, ncells):
+        self.module = weakref.ref(module)
+        self.gen, self.shape, self.tile_bytes, self.grid_dims, self.ncells = gen, shape, tile_bytes, grid_dims, ncells
+
+    def __call__(self, nbrs):
+        m = self.module()
+        if m is None or m._generation != self.gen or tuple(nbrs.shape) != self.shape:
+            return None
+        B, N, K = self.shape
+        dev = nbrs.device
+        L = nat.lib()
+        with torch.no_grad(), torch.cuda.device(dev):
+            t = torch.empty(self.tile_bytes, device=dev, dtype=torch.uint8)
+            nat.check(L.spnb_build_tile_lists(
+                nat.ptr(m.cellIDs), nat.ptr(self.grid_dims), nat.ptr(m.cellStarts), nat.ptr(m.cellEnds),
+                nat.ptr(nbrs), B, N, m.ndim, K, self.ncells, nat.ptr(t), self.tile_bytes, nat.stream()),
+                "spnb_build_tile_lists")
+        return t
 
 
 class ParticleCollision(torch.nn.Module):
@@ -160,6 +193,8 @@ class ParticleCollision(torch.nn.Module):
         dev = locs.device
         L = nat.lib()
         D, G = self.ndim, self.max_grid_dim
+        # the scratch buffers are about to be overwritten: lazy tile builders of earlier calls must refuse
+        self._generation += 1
         ncells = G ** D
 
         ws_bytes = L.spnb_hashgrid_workspace_bytes(batch_size, N, D, G)
@@ -213,30 +248,14 @@ class ParticleCollision(torch.nn.Module):
             tile_bytes = (L.spnb_tile_lists_bytes(batch_size, N, D, self.max_collisions)
                           if qlocs is None and self.tile_lists else 0)
             if tile_bytes > 0:
-                self._generation += 1
-                gen, K = self._generation, self.max_collisions
-
-                def builder(nbrs):
-                    """Compact sidecar of `nbrs` (csrc/tile_lists.cuh).  It is derived from this module's
-                    scratch (sorted keys, cell table), so it can only be built until the next forward()."""
-                    if self._generation != gen or tuple(nbrs.shape) != (batch_size, N, K):
-                        return None
-                    with torch.no_grad(), torch.cuda.device(dev):
-                        t = torch.empty(tile_bytes, device=dev, dtype=torch.uint8)
-                        nat.check(L.spnb_build_tile_lists(
-                            nat.ptr(cellIDs), nat.ptr(grid_dims), nat.ptr(cellStarts), nat.ptr(cellEnds),
-                            nat.ptr(nbrs), batch_size, N, D, K, ncells, nat.ptr(t), tile_bytes, nat.stream()),
-                            "spnb_build_tile_lists")
-                    return t
-
+                builder = _TileBuilder(self, self._generation, (batch_size, N, self.max_collisions), tile_bytes,
+                                       grid_dims, ncells)
                 if self.tile_lists is True:
                     tiles, builder = builder(neighbors), None
         if qlocs is None:
-            # Lists built with the particles as their own queries are symmetric unless one was cut
-            # at max_collisions; ConvSP's backward uses this to avoid atomics.
-            neighbors._spnb_sym_flag = trunc
-            neighbors._spnb_tiles = tiles
-            neighbors._spnb_tile_builder = builder
+            # Lists built with the particles as their own queries are symmetric unless one was cut at
+            # max_collisions or a query lies beyond a clamped grid; ConvSP's backward uses this to avoid atomics.
+            sidecar.attach(neighbors, sidecar.Sidecar(sym_flag=trunc, tiles=tiles, builder=builder))
         self.last_lower_bounds = lower_bounds
         self.last_grid_dims = grid_dims
         if has_data:

@@ -152,7 +152,7 @@ def test_group_oversized_tiles_gather_from_global(spn):
         coll = spn.ParticleCollision(D, 0.1, max_collisions=K, include_self=False).cuda()
         coll.tile_lists = tiles_on
         sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
-        assert int(nb._spnb_sym_flag.item()) == 0
+        assert int(spn.sym_flag_of(nb).item()) == 0
         if tiles_on:
             flag, counts, dec, max_total = tl.decode(spn.tile_lists_of(nb), B, N, K)
             assert flag == 0 and max_total + 1 > tl.TILE_CAP

@@ -43,7 +43,7 @@ def main():
     with torch.no_grad():
         sl, sv, idxs, nb = model.coll(locs, vel)
     nbar = float((nb >= 0).sum().item()) / (B * N)
-    flag = None if args.nosym else nb._spnb_sym_flag
+    flag = None if args.nosym else spn.sym_flag_of(nb)
     peak = 6550.1
     pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pp):
