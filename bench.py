@@ -218,11 +218,17 @@ def time_kernels(torch, spn, model, locs, vel, iters=10):
     low, gd = model.coll.last_lower_bounds, model.coll.last_grid_dims
     coll_out = torch.empty_like(nb)
     tflag = torch.zeros(1, device="cuda", dtype=torch.int32)
-    res["collide"] = (ev_time(lambda: L.spnb_compute_collisions(
-        nat.ptr(sl), nat.ptr(sl), nat.ptr(low), nat.ptr(gd), nat.ptr(model.coll.cellIDs),
-        nat.ptr(model.coll.cellStarts), nat.ptr(model.coll.cellEnds), nat.ptr(coll_out), B, N, N, D, K_NEIGH,
-        model.coll.max_grid_dim ** D, float(RADIUS), float(RADIUS), 0, nat.ptr(tflag), nat.stream())),
-        1, P * (4 * D + 4 + 4 * K_NEIGH))
+    from smoothparticlenets_b200 import sidecar
+    pos4 = sidecar.lookup(sl).pos4
+    tbytes = L.spnb_tile_lists_bytes(B, N, D, K_NEIGH)
+    tbuf = torch.empty(tbytes, device="cuda", dtype=torch.uint8)
+    # cell table + k_collide_tiles: float rows and tile lists from one kernel; bytes: positions and keys read,
+    # 4K bytes of rows + ~2(n-bar+...) bytes of tile rows written
+    res["collide"] = (ev_time(lambda: L.spnb_compute_collisions_tiled(
+        nat.ptr(pos4), nat.ptr(sl), nat.ptr(low), nat.ptr(gd), nat.ptr(model.coll.cellIDs),
+        nat.ptr(model.coll.cellStarts), nat.ptr(model.coll.cellEnds), nat.ptr(coll_out), B, N, D, K_NEIGH,
+        model.coll.max_grid_dim ** D, float(RADIUS), float(RADIUS), 0, nat.ptr(tflag), nat.ptr(tbuf), tbytes,
+        nat.stream())), 1, P * (4 * D + 4 + 4 * K_NEIGH))
     if not getattr(model, "fused", False):
         return res, nbar, {}
 
@@ -230,10 +236,10 @@ def time_kernels(torch, spn, model, locs, vel, iters=10):
     from smoothparticlenets_b200 import convsp_group as cg
     press = torch.rand(B, N, 1, device="cuda")
     groups = {
-        "A": (model.group_a, [ones, sl, ones, sl, ones, ones], 3),
+        "A": (model.group_a, [None, sl, None, sl, None, None], 3),
         "B": (model.group_b, [sl * press, press], 3),
         "C": (model.group_c, [sv], 3),
-        "V": (model.group_v, [sv, ones], 1),
+        "V": (model.group_v, [sv, None], 1),
     }
     fused, reduced = {}, {}
     for name, (grp, datas, per_step) in groups.items():
@@ -243,7 +249,7 @@ def time_kernels(torch, spn, model, locs, vel, iters=10):
         bs_ = [l.bias for l in layers]
         outs = [torch.empty(B, N, c[3], device="cuda") for c in cfg]
         gos = [torch.rand(B, N, c[3], device="cuda") for c in cfg]
-        dds = [torch.empty_like(d) if d is not ones else None for d in datas]
+        dds = [torch.empty_like(d) if d is not None else None for d in datas]
         dl = torch.empty_like(sl)
         afw = cg._layer_array(sl, datas, ws_, bs_, cfg, outs=outs)
         abw = cg._layer_array(sl, datas, ws_, None, cfg, gos=gos, ddatas=dds)
@@ -260,8 +266,10 @@ def time_kernels(torch, spn, model, locs, vel, iters=10):
         # SURVEY 8(d) bytes of the layers this op replaces, and the op's own compulsory bytes
         eq_f = sum(fb(c[2], c[3]) for c in cfg)
         eq_b = sum(bb(c[2], c[3]) for c in cfg)
-        distinct = {id(d): d.shape[2] for d in datas if d is not sl}
+        distinct = {id(d): d.shape[2] for d in datas if d is not None and d is not sl}
         ch_out = sum(c[3] for c in cfg)
+        # the op's own compulsory bytes: positions + distinct data + lists read once, outputs written once
+        # (backward: + grad_out of every layer read, d/dlocs and the data gradients written)
         own_f = 4 * D + 4 * (nbar + 1) + 4 * sum(distinct.values()) + 4 * ch_out
         own_b = own_f + 4 * D + sum(4 * d.shape[2] for d, g_ in zip(datas, dds) if g_ is not None)
         fused["group%s_fwd" % name] = (ev_time(f_fn), per_step, P * eq_f)

@@ -122,7 +122,7 @@ class FluidStep(nn.Module):
             fan = pbf.fanout(new_locs, 8) if hasattr(pbf, "fanout") else (new_locs,) * 8
             xa, xa1, xa2, x1, xb, x2, xc, x3 = fan
             density, nj, ni_s, nj_c, ni_cs, ncount = self.group_a(
-                xa, [ones, xa1, ones, xa2, ones, ones], neighbors)
+                xa, [None, xa1, None, xa2, None, None], neighbors)  # None: data of ones, nothing is read for it
             pressure, xp, nij = pbf.pbf_stage1(x1, density, nj, ni_s, self.stiffness, self.density_rest)
             njp, nip_s = self.group_b(xb, [xp, pressure], neighbors)
             delta0, normals = pbf.pbf_stage2(x2, pressure, nij, njp, nip_s, nj_c, ni_cs, COHESION,
@@ -133,7 +133,7 @@ class FluidStep(nn.Module):
         for _ in range(NUM_ITERATIONS if (self.fused and self.pbf is None) else 0):
             # same data flow as below; layers sharing (new_locs, neighbors) grouped by dependency
             density, nj, ni_s, nj_c, ni_cs, ncount = self.group_a(
-                new_locs, [ones, new_locs, ones, new_locs, ones, ones], neighbors)
+                new_locs, [None, new_locs, None, new_locs, None, None], neighbors)
             nij = new_locs * ni_s - nj
             pressure = self.stiffness * self.relu(density - self.density_rest)
             njp, nip_s = self.group_b(new_locs, [new_locs * pressure, pressure], neighbors)
@@ -171,12 +171,12 @@ class FluidStep(nn.Module):
             new_locs = new_locs + delta
         if self.pbf is not None and hasattr(self.pbf, "pbf_velocity"):
             vel = self.pbf.pbf_velocity(new_locs, self.reorder_un2sort(pidxs, locs), dt)
-            vj, vi_s = self.group_v(new_locs, [vel, ones], neighbors)
+            vj, vi_s = self.group_v(new_locs, [vel, None], neighbors)
             vel = self.pbf.pbf_viscosity(vel, vj, vi_s, dt * VISCOSITY / self.density_rest)
         else:
             vel = (new_locs - self.reorder_un2sort(pidxs, locs)) / dt
             if self.fused:
-                vj, vi_s = self.group_v(new_locs, [vel, ones], neighbors)
+                vj, vi_s = self.group_v(new_locs, [vel, None], neighbors)
                 vi = vel * vi_s
             else:
                 vj = self.spikyD(new_locs, vel, neighbors)

@@ -72,29 +72,31 @@ int spnb_hashgrid_order(const float* locs, const float* low, const float* grid_d
  *   collisions: [batch_size, M, max_collisions] float: accepted particle indices in the reference's
  *   visiting order, then -1 up to the end of the row.
  *   trunc_flag (optional, may be NULL): device int that is atomically OR-ed with 1 if any row was cut
- *   at max_collisions (consumers use it to choose the atomics-free symmetric backward). */
+ *   at max_collisions or a query lies beyond a clamped grid, i.e. the neighbour relation may not be symmetric
+ *   (consumers use it to choose the atomics-free symmetric backward). */
 int spnb_compute_collisions(const float* qlocs, const float* locs, const float* low,
                             const float* grid_dims, const float* cellIDs, float* cellStarts,
                             float* cellEnds, float* collisions, int batch_size, int M, int N,
                             int ndims, int max_collisions, int ncells, float cellEdge, float radius,
                             int include_self, int* trunc_flag, void* stream);
 
-/* Opt-in compact form of the same lists ("tile lists"; layout in
- * smoothparticlenets_b200/csrc/tile_lists.cuh): per 64 consecutive queries the ranges of the sorted
- * order that hold their neighbours (a "tile", staged into shared memory by the ConvSP group kernels with
- * TMA bulk copies) and 16-bit lists of tile slots.  spnb_tile_lists_bytes() is the device buffer size
- * (0: these sizes are not supported -- needs ndims <= 3 and max_collisions a multiple of 16).  spnb_build_tile_lists() derives the
- * buffer from what spnb_hashgrid_order() and spnb_compute_collisions() produced for the particles as
- * their own queries (cellIDs = sorted keys, cellStarts/cellEnds = the cell table, may both be NULL,
- * collisions = [batch_size, N, max_collisions]).  The first int
- * of the buffer is a device-side flag: non-zero = unusable for this call (a list is full / was cut at
- * max_collisions, or a tile exceeds the format's capacities); consumers test it on the device and fall
- * back to the float lists. */
+/* The same lists in two forms from one kernel, for the particles as their own queries (qlocs == locs,
+ * ndims <= 3, max_collisions <= 512): the float rows of spnb_compute_collisions() -- bit-identical -- and the
+ * compact "tile lists" the ConvSP group kernels consume (layout in
+ * smoothparticlenets_b200/csrc/tile_lists.cuh): per 64 consecutive queries the ranges of the sorted order that
+ * hold their neighbours (a "tile", staged into shared memory with TMA bulk copies) and 16-bit lists of tile
+ * slots, stored by list-length rank.  pos4: [batch_size, N, 4] float4 plane of the SORTED positions (x, y, z, 0),
+ * as written by spnb_reorder_data_pos4(); the kernel stages its candidates from it.  tile_lists: device buffer of
+ * spnb_tile_lists_bytes() bytes (0: sizes not supported).  The first int of the buffer is a device-side flag:
+ * non-zero = unusable for this call (bit 0: the neighbour relation may not be symmetric -- a list is full / was
+ * cut at max_collisions, or a query lies beyond a clamped grid; bit 1: a tile exceeds the staging capacity);
+ * consumers test it on the device and fall back to the float lists.  sym_flag (optional) receives bit 0 too. */
 size_t spnb_tile_lists_bytes(int batch_size, int N, int ndims, int max_collisions);
-int spnb_build_tile_lists(const float* cellIDs, const float* grid_dims, const float* cellStarts,
-                          const float* cellEnds, const float* collisions, int batch_size, int N,
-                          int ndims, int max_collisions, int ncells, void* tile_lists,
-                          size_t tile_lists_bytes, void* stream);
+int spnb_compute_collisions_tiled(const float* pos4, const float* locs, const float* low, const float* grid_dims,
+                                  const float* cellIDs, float* cellStarts, float* cellEnds, float* collisions,
+                                  int batch_size, int N, int ndims, int max_collisions, int ncells,
+                                  float cellEdge, float radius, int include_self, int* sym_flag,
+                                  void* tile_lists, size_t tile_lists_bytes, void* stream);
 
 /* Row permutation.  Replaces cuda_reorder_data (gpu_kernels.h:97-111).
  *   reverse == 0: nlocs[b,i] = locs[b,idxs[b,i]];  reverse != 0: nlocs[b,idxs[b,i]] = locs[b,i];
@@ -102,6 +104,11 @@ int spnb_build_tile_lists(const float* cellIDs, const float* grid_dims, const fl
 int spnb_reorder_data(const float* locs, const float* data, const float* idxs, float* nlocs,
                       float* ndata, int batch_size, int N, int ndims, int nchannels, int reverse,
                       void* stream);
+/* reverse == 0 variant that also writes the reordered positions as a float4 plane pos4[b,i] = (x, y, z, 0)
+ * (ndims <= 4): the 16-byte-aligned layout TMA bulk copies and 128-bit shared-memory gathers want. */
+int spnb_reorder_data_pos4(const float* locs, const float* data, const float* idxs, float* nlocs,
+                           float* ndata, float* pos4, int batch_size, int N, int ndims, int nchannels,
+                           void* stream);
 
 /* ---- ConvSP ----------------------------------------------------------------------------------- */
 

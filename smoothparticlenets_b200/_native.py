@@ -24,8 +24,9 @@ _SIGNATURES = {
     "spnb_hashgrid_order": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _f, _i, _vp]),
     "spnb_compute_collisions": (_i, [_vp] * 8 + [_i] * 6 + [_f, _f, _i, _vp, _vp]),
     "spnb_tile_lists_bytes": (_sz, [_i, _i, _i, _i]),
-    "spnb_build_tile_lists": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "spnb_compute_collisions_tiled": (_i, [_vp] * 8 + [_i] * 5 + [_f, _f, _i, _vp, _vp, _sz, _vp]),
     "spnb_reorder_data": (_i, [_vp] * 5 + [_i] * 5 + [_vp]),
+    "spnb_reorder_data_pos4": (_i, [_vp] * 6 + [_i] * 4 + [_vp]),
     "spnb_convsp_forward": (_i, [_vp] * 6 + [_i] * 8 + [_f, _vp, _vp, _i, _i, _vp, _vp]),
     "spnb_convsp_forward_wide_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "spnb_convsp_forward_wide": (_i, [_vp] * 6 + [_i] * 8 + [_f, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),

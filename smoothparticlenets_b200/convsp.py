@@ -55,6 +55,8 @@ class ConvSP(torch.nn.Module):
         # Kept for attribute compatibility (convsp.py:85-86); unused.
         self.nshared_device_mem = -1
         self.device_id = -1
+        # extension: False forces the float-list kernels even where the tile kernels apply
+        self.fast_path = True
 
     def forward(self, locs, data, neighbors, qlocs=None):
         """locs BxNxD, data BxNxC, neighbors BxMxK (float indices, -1 terminated), qlocs BxMxD or
@@ -72,6 +74,14 @@ class ConvSP(torch.nn.Module):
         # 0 = every list is complete, so the relation is symmetric).
         sc = sidecar.lookup(neighbors) if qlocs is None else None
         sym_flag = None if sc is None else sc.sym_flag
+        if (sc is not None and sc.tiles is not None and self.ncells == 1 and self.nchannels <= 4
+                and self.fast_path):
+            # kernel_size 1 on lists that carry tile lists: the single-layer signature of the tile kernels
+            # (csrc/convsp_group.cuh) -- same values within fp32 rounding, no d(weight)
+            from .convsp_group import group_apply
+            out = group_apply([self], locs, [data], neighbors)
+            if out is not None:
+                return out[0]
         neighbors = neighbors.contiguous() if not neighbors.is_contiguous() else neighbors
         return _ConvSPFunction.apply(qlocs, locs, data, neighbors, self.weight, self.bias,
                                      float(self.radius), self.kernel_size, self.dilation,

@@ -9,8 +9,10 @@ data_b, ...], neighbors)`` returns exactly what ``[layer_a(locs, data_a, neighbo
 
 Requirements for the fused path: every layer has kernel_size 1, the same ndim and radius, no query
 locations (the particles are their own queries), no trainable weights that need gradients, and the
-channel layout is one of the compiled-in signatures (csrc/convsp_group.cu).  Anything else silently
-runs the ordinary per-layer path, so the module is always safe to use.
+layer list is one of the compiled-in signatures (csrc/convsp_group_inst_*.cu: the groups of the fluid
+step, and ANY single layer with up to 4 input channels).  Anything else silently runs the ordinary
+per-layer path, so the module is always safe to use.  A data entry may be None: a one-channel layer
+whose data is all ones (density, neighbour count) then reads no data at all.
 """
 import ctypes
 
@@ -35,27 +37,48 @@ class ConvSPGroup(torch.nn.Module):
                              for l in layers))
 
     def forward(self, locs, datas, neighbors):
-        """locs BxNxD, datas: one BxNxC_l tensor per layer, neighbors BxNxK.  Returns a tuple with one
+        """locs BxNxD, datas: one BxNxC_l tensor per layer -- or None for a one-channel layer whose data is all
+        ones (a density / neighbour count: nothing is read for it) --, neighbors BxNxK.  Returns a tuple with one
         BxNxO_l tensor per layer."""
         layers = list(self.layers)
         if len(datas) != len(layers):
             raise ValueError("ConvSPGroup: expected %d data tensors, got %d" % (len(layers), len(datas)))
-        fused = self._fusable and locs.is_cuda and neighbors.shape[1] == locs.shape[1]
-        if fused:
-            for l in layers:
-                if l.weight.requires_grad and torch.is_grad_enabled():
-                    fused = False  # d(weight) is only produced by the per-layer kernels
-        if fused:
-            locs_c = locs.contiguous()
-            datas_c = [d.contiguous() for d in datas]
-            sym_flag = sym_flag_of(neighbors)
-            tiles = tile_lists_of(neighbors)
-            cfg = tuple((l.kernel_fn, l.dis_norm, l.nchannels, l.nkernels) for l in layers)
-            flat = list(datas_c) + [l.weight for l in layers] + [l.bias for l in layers]
-            if _supported(locs_c, datas_c, layers, cfg):
-                return _ConvSPGroupFunction.apply(locs_c, neighbors.contiguous(), (sym_flag, tiles),
-                                                  float(layers[0].radius), cfg, *flat)
-        return tuple(l(locs, d, neighbors) for l, d in zip(layers, datas))
+        for l, d in zip(layers, datas):
+            if d is None and l.nchannels != 1:
+                raise ValueError("ConvSPGroup: data=None (ones) needs a layer with one input channel")
+        out = group_apply(layers, locs, datas, neighbors) if self._fusable else None
+        if out is not None:
+            return out
+        B, N = locs.shape[0], locs.shape[1]
+        ones = None
+        res = []
+        for l, d in zip(layers, datas):
+            if d is None:
+                if ones is None:
+                    ones = torch.ones(B, N, 1, device=locs.device, dtype=locs.dtype)
+                d = ones
+            res.append(l(locs, d, neighbors))
+        return tuple(res)
+
+
+def group_apply(layers, locs, datas, neighbors):
+    """The fused evaluation of `layers` (all kernel_size 1, same ndim and radius) on (locs, neighbors), or None when
+    it does not apply: CPU tensors, separate query locations, weights that need gradients (d(weight) is only
+    produced by the per-layer kernels), or a channel layout that is not compiled in."""
+    if not (locs.is_cuda and neighbors.dim() == 3 and neighbors.shape[1] == locs.shape[1]):
+        return None
+    if torch.is_grad_enabled() and any(l.weight.requires_grad for l in layers):
+        return None
+    locs_c = locs.contiguous()
+    datas_c = [None if d is None else d.contiguous() for d in datas]
+    cfg = tuple((l.kernel_fn, l.dis_norm, l.nchannels, l.nkernels) for l in layers)
+    if not _supported(locs_c, datas_c, layers, cfg):
+        return None
+    sym_flag = sym_flag_of(neighbors)
+    tiles = tile_lists_of(neighbors)
+    flat = list(datas_c) + [l.weight for l in layers] + [l.bias for l in layers]
+    return _ConvSPGroupFunction.apply(locs_c, neighbors.contiguous(), (sym_flag, tiles), float(layers[0].radius), cfg,
+                                      *flat)
 
 
 def _layer_array(locs, datas, weights, biases, cfg, outs=None, gos=None, ddatas=None):
@@ -90,7 +113,8 @@ class _ConvSPGroupFunction(torch.autograd.Function):
         n = len(cfg)
         datas, weights, biases = flat[:n], flat[n:2 * n], flat[2 * n:3 * n]
         for t in (locs, neighbors) + tuple(flat):
-            nat.require_cuda_f32(t, "ConvSPGroup operand")
+            if t is not None:
+                nat.require_cuda_f32(t, "ConvSPGroup operand")
         B, N, D = locs.shape
         K = neighbors.shape[2]
         L = nat.lib()
@@ -102,7 +126,8 @@ class _ConvSPGroupFunction(torch.autograd.Function):
             nat.check(L.spnb_convsp_group_forward(nat.ptr(locs), nat.ptr(neighbors), B, N, D, K, radius, n,
                                                   arr, nat.ptr(ws), wsb, nat.ptr(tiles), nat.stream()),
                       "spnb_convsp_group_forward")
-        ctx.save_for_backward(locs, neighbors, *datas, *weights)
+        ctx.has_data = [d is not None for d in datas]
+        ctx.save_for_backward(locs, neighbors, *[d for d in datas if d is not None], *weights)
         ctx.cfg, ctx.radius, ctx.sym_flag, ctx.tiles = cfg, radius, sym_flag, tiles
         return tuple(outs)
 
@@ -112,16 +137,19 @@ class _ConvSPGroupFunction(torch.autograd.Function):
         n = len(cfg)
         saved = ctx.saved_tensors
         locs, neighbors = saved[0], saved[1]
-        datas, weights = saved[2:2 + n], saved[2 + n:2 + 2 * n]
+        nd = sum(ctx.has_data)
+        it = iter(saved[2:2 + nd])
+        datas = [next(it) if h else None for h in ctx.has_data]
+        weights = saved[2 + nd:2 + nd + n]
         B, N, D = locs.shape
         K = neighbors.shape[2]
         dev = locs.device
         gos = [g.contiguous() if g is not None else torch.zeros(B, N, cfg[i][3], device=dev)
                for i, g in enumerate(grad_outs)]
         need_locs = ctx.needs_input_grad[0]
-        need_data = ctx.needs_input_grad[5:5 + n]
         dlocs = torch.empty(B, N, D, device=dev, dtype=torch.float32)
-        ddatas = [torch.empty_like(datas[i]) if need_data[i] else None for i in range(n)]
+        # every data TENSOR gets its gradient buffer (the compiled signatures do not depend on requires_grad)
+        ddatas = [torch.empty_like(d) if d is not None else None for d in datas]
         L = nat.lib()
         arr = _layer_array(locs, datas, weights, None, cfg, gos=gos, ddatas=ddatas)
         wsb = L.spnb_convsp_group_workspace_bytes(nat.ptr(locs), B, N, D, radius, n, arr, 1)
@@ -131,5 +159,7 @@ class _ConvSPGroupFunction(torch.autograd.Function):
                                                    arr, nat.ptr(dlocs), nat.ptr(ctx.sym_flag), nat.ptr(ws),
                                                    wsb, nat.ptr(ctx.tiles), nat.stream()),
                       "spnb_convsp_group_backward")
+        need_data = ctx.needs_input_grad[5:5 + n]
+        ddatas = [g if need_data[i] else None for i, g in enumerate(ddatas)]
         dbias = [gos[i].sum(1).sum(0) if ctx.needs_input_grad[5 + 2 * n + i] else None for i in range(n)]
         return (dlocs if need_locs else None, None, None, None, None) + tuple(ddatas) + (None,) * n + tuple(dbias)

@@ -18,6 +18,7 @@
 //  * neighbour lists: one warp per 8 consecutive queries; queries in the same cell share a candidate
 //    set that is resolved once and staged in shared memory, hits are compacted with ballot/popc so
 //    rows are written coalesced, including the -1 padding.
+#include "list_walk.cuh"
 #include "spnb_common.cuh"
 #include "tile_lists.cuh"
 
@@ -333,26 +334,87 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
 }
 
 // ---- reorder -------------------------------------------------------------------------------------
-// One thread per output float of one tensor (z = 0: locs, z = 1: data), blockIdx.y = scene, 32-bit
-// index math with a compile-time row width where it is small.  reverse == 0: out[i,:] = in[idxs[i],:]
-// (coalesced writes, row gathers); else out[idxs[i],:] = in[i,:].
-template <int WT>
+// reverse == 0: out[i,:] = in[idxs[i],:]   (row gathers, coalesced writes)
+// reverse != 0: out[idxs[i],:] = in[i,:]   (coalesced reads, row scatters)
+// blockIdx.y = scene, blockIdx.z = tensor (0: locs, 1: data).
+//
+// Rows of 1..4 floats (positions, velocities, scalars): one thread per row; the contiguous side of the copy
+// goes through a per-warp shared-memory transpose so that it moves as 128-bit accesses of a whole warp (32
+// rows of W floats are 8*W float4), the permuted side is W scalar accesses per row.  With `pos4` the
+// gathered position rows are also written as a float4 plane (x, y, z, 0): the layout TMA bulk copies and
+// LDS.128 gathers want (k_collide_tiles and the ConvSP tile kernels stage it).
+template <int W>
 __global__ void __launch_bounds__(256)
-k_reorder(const float* __restrict__ locs, const float* __restrict__ data,
-          const float* __restrict__ idxs, float* __restrict__ nlocs, float* __restrict__ ndata, int N,
-          int D, int C, int reverse)
+k_reorder_rows(const float* __restrict__ locs, const float* __restrict__ data, const float* __restrict__ idxs,
+               float* __restrict__ nlocs, float* __restrict__ ndata, float4* __restrict__ pos4, int N, int reverse)
 {
+    __shared__ __align__(16) float s_t[8][32 * W];
     const bool is_loc = blockIdx.z == 0;
-    const int W = WT > 0 ? WT : (is_loc ? D : C);
-    const float* __restrict__ in = (is_loc ? locs : data) + (size_t)blockIdx.y * N * W;
-    float* __restrict__ out = (is_loc ? nlocs : ndata) + (size_t)blockIdx.y * N * W;
-    const float* __restrict__ ix = idxs + (size_t)blockIdx.y * N;
-    const unsigned total = (unsigned)N * (unsigned)W;
+    const size_t sb = (size_t)blockIdx.y * N;
+    const float* __restrict__ in = (is_loc ? locs : data) + sb * W;
+    float* __restrict__ out = (is_loc ? nlocs : ndata) + sb * W;
+    const float* __restrict__ ix = idxs + sb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i0 = (blockIdx.x * 8 + warp) * 32;  // first row of this warp
+    if (i0 >= N) return;
+    const int i = i0 + lane;
+    const bool live = i < N;
+    const int other = live ? (int)ix[i] : 0;
+    // the contiguous side can move as float4 when the warp's 32 rows are all there and 16-byte aligned
+    const bool vec = i0 + 32 <= N && ((reinterpret_cast<size_t>(in) | reinterpret_cast<size_t>(out)) & 15) == 0 &&
+                     (((size_t)N * W) & 3) == 0;
+    float* st = s_t[warp];
+    float r[W];
+    if (!reverse) {
+#pragma unroll
+        for (int k = 0; k < W; ++k) r[k] = live ? in[(size_t)other * W + k] : 0.0f;
+        if (pos4 != nullptr && is_loc && live)
+            pos4[sb + i] = make_float4(r[0], W > 1 ? r[1] : 0.0f, W > 2 ? r[2] : 0.0f, 0.0f);
+        if (vec) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) st[lane * W + k] = r[k];
+            __syncwarp();
+            if (lane < 8 * W)
+                reinterpret_cast<float4*>(out + (size_t)i0 * W)[lane] = reinterpret_cast<const float4*>(st)[lane];
+        } else if (live) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) out[(size_t)i * W + k] = r[k];
+        }
+    } else {
+        if (vec) {
+            if (lane < 8 * W)
+                reinterpret_cast<float4*>(st)[lane] = reinterpret_cast<const float4*>(in + (size_t)i0 * W)[lane];
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < W; ++k) r[k] = st[lane * W + k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < W; ++k) r[k] = live ? in[(size_t)i * W + k] : 0.0f;
+        }
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < W; ++k) out[(size_t)other * W + k] = r[k];
+        }
+    }
+}
+
+// Wider rows: one thread per 16-byte piece of a row when W is a multiple of 4 (VEC), else per float.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+k_reorder_wide(const float* __restrict__ in_, const float* __restrict__ idxs, float* __restrict__ out_, int N,
+               int W, int reverse)
+{
+    const int P = VEC ? W / 4 : W;  // pieces per row
+    const size_t sb = (size_t)blockIdx.y * N;
+    const float* __restrict__ ix = idxs + sb;
+    const unsigned total = (unsigned)N * (unsigned)P;
     for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const unsigned row = e / (unsigned)W, col = e - row * (unsigned)W;
+        const unsigned row = e / (unsigned)P, col = e - row * (unsigned)P;
         const unsigned other = (unsigned)(int)ix[row];
-        if (reverse) out[other * W + col] = in[e];
-        else out[e] = in[other * W + col];
+        const size_t a = (sb + (reverse ? row : other)) * P + col;   // source piece
+        const size_t d = (sb + (reverse ? other : row)) * P + col;   // destination piece
+        if (VEC) reinterpret_cast<float4*>(out_)[d] = reinterpret_cast<const float4*>(in_)[a];
+        else out_[d] = in_[a];
     }
 }
 
@@ -388,118 +450,6 @@ k_table_fill(const uint32_t* __restrict__ keys, const float* __restrict__ grid_d
     if (i == N - 1 && c < (uint32_t)n) ends[(size_t)b * ncells + c] = (float)N;
 }
 
-// ---- tile descriptors (tile_lists.cuh) -------------------------------------------------------------
-// One warp per tile block of kTileQ consecutive sorted queries: the block's cells span the keys
-// [cf, cl]; for every offset o of the leading D-1 grid dimensions its neighbours lie in the cells
-// [cf+o-1, cl+o+1] (a superset: cells that wrap around a grid border only add candidates that fail the
-// distance test or are never referenced).  Each lane turns one such cell interval into a range of the
-// sorted order with two binary searches over the sorted keys; lane 0 sorts and merges the ranges.
-__device__ __forceinline__ int key_lower_bound(const uint32_t* __restrict__ k, int N, long long v)
-{
-    int lo = 0, hi = N;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((long long)k[mid] < v) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo;
-}
-
-__global__ void __launch_bounds__(256)
-k_tile_ranges(const uint32_t* __restrict__ keys, const float* __restrict__ grid_dims,
-              const float* __restrict__ starts, const float* __restrict__ ends, int N, int D,
-              int ncells, int ntb, TileDesc* __restrict__ descs, int* flag)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tb = blockIdx.x * 8 + warp, b = blockIdx.y;
-    if (tb >= ntb) return;
-    const uint32_t* k = keys + (size_t)b * N;
-    const float* gd = grid_dims + b * D;
-    long long used = 1;
-    for (int d = 0; d < D; ++d) used *= (long long)gd[d];
-    if (used > ncells) used = ncells;
-    const int q0 = tb * kTileQ, q1 = min(q0 + kTileQ, N) - 1;
-    const long long cf = k[q0], cl = k[q1];
-    const int sy = (int)gd[D - 1];
-    const int sx = D >= 3 ? sy * (int)gd[D - 2] : 0;
-    int nrange = 1;
-    for (int d = 1; d < D; ++d) nrange *= 3;
-    int s = 0, e = 0;
-    if (lane < nrange) {
-        long long o = 0;
-        if (D == 2) o = (long long)(lane - 1) * sy;
-        if (D == 3) o = (long long)(lane % 3 - 1) * sy + (long long)(lane / 3 - 1) * sx;
-        long long lo = cf + o - 1, hi = cl + o + 1;
-        if (lo < 0) lo = 0;
-        if (hi > used - 1) hi = used - 1;
-        if (lo <= hi) {
-            if (starts != nullptr && hi - lo < 64) {
-                // the cell table answers both bounds with one load each unless border cells are empty
-                // (empty cells read start == end == 0)
-                const float* st = starts + (size_t)b * ncells;
-                const float* en = ends + (size_t)b * ncells;
-                long long c0 = lo, c1 = hi;
-                while (c0 <= hi && !(en[c0] > st[c0])) ++c0;
-                while (c1 >= c0 && !(en[c1] > st[c1])) --c1;
-                if (c0 <= c1) {
-                    s = (int)st[c0];
-                    e = (int)en[c1];
-                }
-            } else {
-                s = key_lower_bound(k, N, lo);
-                e = key_lower_bound(k, N, hi + 1);
-            }
-        }
-    }
-    int rs[kTileMaxRanges], re[kTileMaxRanges];
-#pragma unroll
-    for (int r = 0; r < kTileMaxRanges; ++r) {
-        rs[r] = __shfl_sync(0xffffffffu, s, r);
-        re[r] = __shfl_sync(0xffffffffu, e, r);
-    }
-    if (lane != 0) return;
-    // insertion sort by start (empty ranges last), then merge overlaps
-    int n = 0;
-    int ss[kTileMaxRanges], ee[kTileMaxRanges];
-    for (int r = 0; r < nrange; ++r) {
-        if (re[r] <= rs[r]) continue;
-        int p = n++;
-        while (p > 0 && ss[p - 1] > rs[r]) {
-            ss[p] = ss[p - 1];
-            ee[p] = ee[p - 1];
-            --p;
-        }
-        ss[p] = rs[r];
-        ee[p] = re[r];
-    }
-    TileDesc d;
-    d.nr = 0;
-    int total = 0;
-    for (int r = 0; r < kTileMaxRanges; ++r) d.start[r] = d.prefix[r] = 0;
-    int cur_s = 0, cur_e = -1;
-    for (int r = 0; r <= n; ++r) {
-        if (r < n && cur_e >= 0 && ss[r] <= cur_e) {
-            if (ee[r] > cur_e) cur_e = ee[r];
-            continue;
-        }
-        if (cur_e >= 0) {
-            d.start[d.nr] = cur_s;
-            d.prefix[d.nr] = total;
-            total += cur_e - cur_s;
-            ++d.nr;
-        }
-        if (r < n) {
-            cur_s = ss[r];
-            cur_e = ee[r];
-        }
-    }
-    d.prefix[d.nr] = total;
-    for (int r = d.nr + 1; r <= kTileMaxRanges; ++r) d.prefix[r] = total;
-    d.total = total;
-    for (int i = 0; i < 11; ++i) d.pad[i] = 0;
-    descs[(size_t)b * ntb + tb] = d;
-}
-
 // ---- neighbour lists -----------------------------------------------------------------------------
 // One warp per kQPW consecutive queries.  Consecutive queries that fall in the same grid cell (all of
 // them, when the queries are the cell-sorted particles themselves) share one candidate set: the
@@ -509,41 +459,36 @@ k_tile_ranges(const uint32_t* __restrict__ keys, const float* __restrict__ grid_
 // coalesced row writes, -1 padding.  Cells are visited in the reference's odometer order over
 // {-1,0,1}^D with dimension 0 fastest and candidates inside a cell in sorted order
 // (common_funcs.h:906-943), so rows are bit-identical to the reference's, truncation included.
+//
+// This is the general routine (separate query locations, any ndims, any K).  When the particles are their
+// own queries k_collide_tiles below produces the same rows from shared-memory tiles, together with the
+// compact tile lists.
 #ifndef SPNB_COLLIDE_QPW
 #define SPNB_COLLIDE_QPW 16  // measured: 8 -> 318 us, 16 -> 304 us, 32 -> 306 us at c2 (longer same-cell runs share one candidate staging)
 #endif
 constexpr int kQPW = SPNB_COLLIDE_QPW;  // queries per warp (<= 32)
 constexpr int kCollideWarps = 8;  // warps per block
 
-template <int DT>
-__global__ void __launch_bounds__(kCollideWarps * 32)
-k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
-          const float* __restrict__ low, const float* __restrict__ grid_dims,
-          const float* __restrict__ starts, const float* __restrict__ ends,
-          float* __restrict__ coll, int M, int N, int ndims, int K, int ncells, float edge, float r2,
-          int include_self, int* trunc_flag)
-{
-    constexpr int MD = DT > 0 ? DT : SPNB_MAXD;
-    constexpr int CM = DT > 0 ? 256 : 64;  // staged candidates per window
-    const int D = DT > 0 ? DT : ndims;
-    __shared__ int s_off[kCollideWarps][33];
-    __shared__ int s_start[kCollideWarps][32];
-    __shared__ int s_idx[kCollideWarps][CM];
-    __shared__ float s_y[kCollideWarps][MD][CM];
-    __shared__ int s_found[kCollideWarps][kQPW];
+template <int MD, int CM>
+struct CollideSmem {
+    int off[kCollideWarps][33];
+    int start[kCollideWarps][32];
+    int idx[kCollideWarps][CM];
+    float y[kCollideWarps][MD][CM];
+    int found[kCollideWarps][kQPW];
+};
 
+// Rows of the nq queries starting at sq (their rows start at `rows`), for one warp.  Returns true when the
+// neighbour relation may not be symmetric (a row was cut at K, or a query lies beyond a clamped grid).
+template <int DT, int MD, int CM>
+__device__ __forceinline__ bool collide_rows_warp(CollideSmem<MD, CM>& sm, const float* __restrict__ sq,
+                                                  const float* __restrict__ sl, float* __restrict__ rows, int nq,
+                                                  const float* __restrict__ lo, const float* __restrict__ gd,
+                                                  const float* __restrict__ st, const float* __restrict__ en, int ndims,
+                                                  int K, int ncells, float edge, float r2, int include_self)
+{
+    const int D = DT > 0 ? DT : ndims;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y;
-    const int q0 = (blockIdx.x * kCollideWarps + warp) * kQPW;
-    if (q0 >= M) return;
-    const int nq = min(kQPW, M - q0);
-    const float* gd = grid_dims + b * D;
-    const float* lo = low + b * D;
-    const float* sl = locs + (size_t)b * N * D;
-    const float* sq = qlocs + ((size_t)b * M + q0) * D;
-    float* rows = coll + ((size_t)b * M + q0) * K;
-    const float* st = starts + (size_t)b * ncells;
-    const float* en = ends + (size_t)b * ncells;
     int total_cells = 1;
 #pragma unroll
     for (int k = 0; k < D; ++k) total_cells *= 3;
@@ -561,15 +506,15 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
             for (int k = 0; k < D; ++k)
                 same = same && grid_coord_of(sq[(qi + lane) * D + k], lo[k], edge) == gc[k];
         }
-        const unsigned sm = __ballot_sync(0xffffffffu, same);
-        const int run = __ffs(~sm) - 1;  // leading ones (lane 0 always matches itself)
+        const unsigned smk = __ballot_sync(0xffffffffu, same);
+        const int run = __ffs(~smk) - 1;  // leading ones (lane 0 always matches itself)
         // A query two or more cells past the upper border of a clamped grid sees no cell at all, while the
         // border cell it was hashed into (partial_grid_hash clamps, loc2grid does not: common_funcs.h:96-119,
         // 913-914) is still scanned by its neighbours: the relation is then not symmetric.
 #pragma unroll
         for (int k = 0; k < D; ++k)
             if (gd[k] > 0.0f && (float)gc[k] >= gd[k] + 1.0f) truncated = true;
-        if (lane < run) s_found[warp][lane] = 0;
+        if (lane < run) sm.found[warp][lane] = 0;
         __syncwarp();
 
         for (int cell0 = 0; cell0 < total_cells; cell0 += 32) {
@@ -600,9 +545,9 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
             }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
             __syncwarp();
-            s_off[warp][lane + 1] = incl;
-            if (lane == 0) s_off[warp][0] = 0;
-            s_start[warp][lane] = cstart;
+            sm.off[warp][lane + 1] = incl;
+            if (lane == 0) sm.off[warp][0] = 0;
+            sm.start[warp][lane] = cstart;
             __syncwarp();
 
             for (int w0 = 0; w0 < total; w0 += CM) {
@@ -610,19 +555,19 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
                 const int wn = min(CM, total - w0);
                 for (int t = lane; t < wn; t += 32) {
                     const int tt = w0 + t;
-                    int c = 0;  // largest c with s_off[c] <= tt
+                    int c = 0;  // largest c with off[c] <= tt
 #pragma unroll
-                    for (int s = 16; s > 0; s >>= 1)
-                        if (s_off[warp][c + s] <= tt) c += s;
-                    const int idx = s_start[warp][c] + (tt - s_off[warp][c]);
-                    s_idx[warp][t] = idx;
+                    for (int s_ = 16; s_ > 0; s_ >>= 1)
+                        if (sm.off[warp][c + s_] <= tt) c += s_;
+                    const int idx = sm.start[warp][c] + (tt - sm.off[warp][c]);
+                    sm.idx[warp][t] = idx;
 #pragma unroll
-                    for (int k = 0; k < D; ++k) s_y[warp][k][t] = sl[(size_t)idx * D + k];
+                    for (int k = 0; k < D; ++k) sm.y[warp][k][t] = sl[(size_t)idx * D + k];
                 }
                 __syncwarp();
                 // ---- every query of the run scans the window
                 for (int r = 0; r < run; ++r) {
-                    int found = s_found[warp][r];
+                    int found = sm.found[warp][r];
                     if (found >= K) continue;
                     float x[MD];
 #pragma unroll
@@ -636,25 +581,25 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
                             float d = 0.0f;
 #pragma unroll
                             for (int k = 0; k < D; ++k) {
-                                const float nr = x[k] - s_y[warp][k][t];
+                                const float nr = x[k] - sm.y[warp][k][t];
                                 d += nr * nr;
                             }
                             hit = d < r2 && (d > 0.0f || include_self);
-                            idx = s_idx[warp][t];
+                            idx = sm.idx[warp][t];
                         }
                         const unsigned m = __ballot_sync(0xffffffffu, hit);
                         const int pos = found + __popc(m & lanemask_lt());
                         if (hit && pos < K) row[pos] = (float)idx;
                         found += __popc(m);
                     }
-                    if (lane == 0) s_found[warp][r] = found;
+                    if (lane == 0) sm.found[warp][r] = found;
                 }
                 __syncwarp();
             }
         }
         // ---- terminate / pad the rows of the run
         for (int r = 0; r < run; ++r) {
-            int found = s_found[warp][r];
+            int found = sm.found[warp][r];
             if (found >= K) {
                 truncated = true;
                 found = K;
@@ -665,105 +610,464 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
         __syncwarp();
         qi += run;
     }
+    return truncated;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kCollideWarps * 32)
+k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
+          const float* __restrict__ low, const float* __restrict__ grid_dims,
+          const float* __restrict__ starts, const float* __restrict__ ends,
+          float* __restrict__ coll, int M, int N, int ndims, int K, int ncells, float edge, float r2,
+          int include_self, int* trunc_flag)
+{
+    constexpr int MD = DT > 0 ? DT : SPNB_MAXD;
+    constexpr int CM = DT > 0 ? 256 : 64;  // staged candidates per window
+    const int D = DT > 0 ? DT : ndims;
+    __shared__ CollideSmem<MD, CM> sm;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int q0 = (blockIdx.x * kCollideWarps + warp) * kQPW;
+    if (q0 >= M) return;
+    const bool truncated = collide_rows_warp<DT, MD, CM>(
+        sm, qlocs + ((size_t)b * M + q0) * D, locs + (size_t)b * N * D, coll + ((size_t)b * M + q0) * K,
+        min(kQPW, M - q0), low + b * D, grid_dims + b * D, starts + (size_t)b * ncells, ends + (size_t)b * ncells,
+        ndims, K, ncells, edge, r2, include_self);
     if (truncated && trunc_flag && lane == 0) atomicOr(trunc_flag, 1);
 }
 
-// ---- tile lists (tile_lists.cuh) ---------------------------------------------------------------------
-// One block per tile block of 64 queries, run after k_collide on the float rows it wrote: every warp
-// reads the rows of 8 queries (four rows at a time, 128 bytes of each per step, up to the terminator),
-// maps each neighbour index to its slot in the block's candidate ranges (TileDesc: ascending range
-// starts kept in registers) and writes the 16-bit entry, the sentinel padding of the last unit and the
-// list length.
-constexpr int kBuildThreads = 256;
+// ---- neighbour lists + tile lists in one kernel (particles are their own queries, ndims <= 3) -------------
+// One CTA per tile block of kTileQ = 64 consecutive sorted queries (tile_lists.cuh):
+//  1. warp 0 derives the block's candidate ranges (TileDesc): the block's cells span the keys [cf, cl]; for every
+//     offset o of the leading D-1 grid dimensions its neighbours lie in the cells [cf+o-1, cl+o+1] (a superset:
+//     cells that wrap around a grid border only add candidates that fail the distance test).  Each lane turns one
+//     such cell interval into a range of the sorted order through the cell table; the ranges are ranked and
+//     merged with shuffles;
+//  2. the float4 position plane of those ranges is staged into shared memory with TMA bulk copies (one
+//     cp.async.bulk per range, completion on an mbarrier), so every candidate is an LDS.128 away;
+//  3. each warp takes 8 queries.  Per run of queries sharing a cell the 3^D neighbour cells are resolved once
+//     (lane per cell), turned into tile slots and loaded -- 256 candidates at a time -- into REGISTERS (slot and
+//     coordinates, 8 per lane); every query of the run then tests them with the reference's exact predicate
+//     and order (odometer over the cells with dimension 0 fastest, ascending index inside a cell:
+//     common_funcs.h:906-943) and appends the hits' slots to its row in shared memory (ballot / popc);
+//  4. the block then ranks its queries by list length and writes, from the same hits, the float rows
+//     (coalesced 128-byte lines incl. the -1 padding) and the 16-bit tile rows of every octile.
+// A block whose ranges do not fit the staged tile reads its candidates from global memory; only a block with more
+// than kTileMaxSlots candidates (a dense clump) computes its rows with collide_rows_warp and raises the tile flag.
+constexpr int kCtThreads = 256;
+constexpr int kCtWin = 256;  // candidates held in registers per window (8 per lane)
 
-__global__ void __launch_bounds__(kBuildThreads)
-k_tile_build(const float* __restrict__ coll, const TileDesc* __restrict__ descs, int N, int K, int ntb,
-             int* __restrict__ tile_flag, int* __restrict__ tcounts, unsigned short* __restrict__ tlists)
+__device__ __forceinline__ int key_lower_bound(const uint32_t* __restrict__ k, int N, long long v)
 {
+    int lo = 0, hi = N;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)k[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// Executed by one full warp; fills nr / total / start / prefix of *d (shared memory).
+__device__ __forceinline__ void tile_desc_warp(const uint32_t* __restrict__ k, const float* __restrict__ gd,
+                                               const float* __restrict__ st, const float* __restrict__ en, int N, int D,
+                                               int ncells, int q0, int nq, TileDesc* d)
+{
+    const int lane = threadIdx.x & 31;
+    long long used = 1;
+    for (int i = 0; i < D; ++i) used *= (long long)gd[i];
+    if (used > ncells) used = ncells;
+    const long long cf = k[q0], cl = k[q0 + nq - 1];
+    const int sy = (int)gd[D - 1];
+    const int sx = D >= 3 ? sy * (int)gd[D - 2] : 0;
+    int nrange = 1;
+    for (int i = 1; i < D; ++i) nrange *= 3;
+    int s = 0, e = 0;
+    if (lane < nrange) {
+        long long o = 0;
+        if (D == 2) o = (long long)(lane - 1) * sy;
+        if (D == 3) o = (long long)(lane % 3 - 1) * sy + (long long)(lane / 3 - 1) * sx;
+        long long lo = cf + o - 1, hi = cl + o + 1;
+        if (lo < 0) lo = 0;
+        if (hi > used - 1) hi = used - 1;
+        if (lo <= hi) {
+            if (hi - lo < 64) {
+                // the cell table answers both bounds with one load each unless border cells are empty
+                // (empty cells read start == end == 0)
+                long long c0 = lo, c1 = hi;
+                while (c0 <= hi && !(en[c0] > st[c0])) ++c0;
+                while (c1 >= c0 && !(en[c1] > st[c1])) --c1;
+                if (c0 <= c1) {
+                    s = (int)st[c0];
+                    e = (int)en[c1];
+                }
+            } else {
+                s = key_lower_bound(k, N, lo);
+                e = key_lower_bound(k, N, hi + 1);
+            }
+        }
+    }
+    if (e > N) e = N;
+    const bool have = lane < nrange && e > s;
+    // rank of my range among the non-empty ones, by start
+    int rank = 0;
+#pragma unroll
+    for (int r = 0; r < kTileMaxRanges; ++r) {
+        const int os = __shfl_sync(0xffffffffu, s, r);
+        const bool oh = __shfl_sync(0xffffffffu, (int)have, r) != 0;
+        if (oh && (os < s || (os == s && r < lane))) ++rank;
+    }
+    const unsigned hm = __ballot_sync(0xffffffffu, have);
+    const int n = __popc(hm);
+    // gather the sorted ranges into lanes 0..n-1
+    int ss = 0, ee = 0;
+#pragma unroll
+    for (int r = 0; r < kTileMaxRanges; ++r) {
+        const int os = __shfl_sync(0xffffffffu, s, r), oe = __shfl_sync(0xffffffffu, e, r);
+        const int orank = __shfl_sync(0xffffffffu, rank, r);
+        const bool oh = (hm >> r) & 1u;
+        if (oh && orank == lane) {
+            ss = os;
+            ee = oe;
+        }
+    }
+    // merge overlapping / touching ranges: running maximum of the ends, a range starts a new group when its
+    // start lies beyond every earlier end
+    int me = ee;  // inclusive prefix maximum of ends over lanes 0..lane
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, me, o);
+        if (lane >= o && lane < n) me = max(me, v);
+    }
+    const int prev_max = __shfl_up_sync(0xffffffffu, me, 1);
+    const bool head = lane < n && (lane == 0 || ss > prev_max);
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const int nr = __popc(heads);
+    const int grp = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;  // group of my range (lane < n)
+    // end of a group = prefix maximum at its last member = value at the lane before the next head (or n-1)
+    int gs = 0, ge = 0;  // lane g < nr: merged range g
+    {
+        // lane g finds the g-th head
+        unsigned hmask = heads;
+        int hl = 0;
+        for (int i = 0; i <= lane && i < nr; ++i) {
+            hl = __ffs(hmask) - 1;
+            hmask &= hmask - 1;
+        }
+        const int next = (lane < nr && hmask) ? __ffs(hmask) - 1 : n;  // first lane of the next group
+        const int s_h = __shfl_sync(0xffffffffu, ss, lane < nr ? hl : 0);
+        const int e_l = __shfl_sync(0xffffffffu, me, lane < nr ? max(next - 1, 0) : 0);
+        if (lane < nr) {
+            gs = s_h;
+            ge = e_l;
+        }
+    }
+    (void)grp;
+    int len = lane < nr ? ge - gs : 0;
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 15);
+    if (lane < kTileMaxRanges) {
+        d->start[lane] = lane < nr ? gs : 0;
+        d->prefix[lane] = lane < nr ? incl - len : total;
+    }
+    if (lane == 0) {
+        d->nr = nr;
+        d->total = total;
+        d->prefix[kTileMaxRanges] = total;
+    }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kCtThreads)
+k_collide_tiles(const float4* __restrict__ pos4, const float* __restrict__ locs, const float* __restrict__ low,
+                const float* __restrict__ grid_dims, const uint32_t* __restrict__ keys,
+                const float* __restrict__ starts, const float* __restrict__ ends, float* __restrict__ coll, int N,
+                int K, int ncells, float edge, float r2, int include_self, int* sym_flag, int* tile_flag,
+                TileDesc* __restrict__ descs, unsigned char* __restrict__ blobs, size_t blob_stride, int ntb)
+{
+    constexpr int D = DT;
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    float4* s_pos = reinterpret_cast<float4*>(s_raw);                                  // [kTileCap]
+    int* s_slot2idx = reinterpret_cast<int*>(s_raw + kTileCap * 16);                   // [kTileCap]
+    unsigned short* s_cand = reinterpret_cast<unsigned short*>(s_raw + kTileCap * 20); // [8][kCtWin]
+    unsigned short* s_hits = s_cand + 8 * kCtWin;                                      // [kTileQ][K]
     __shared__ TileDesc s_desc;
-    __shared__ int s_fwd[kTileMaxRanges], s_len[kTileMaxRanges];  // idx -> slot: idx + s_fwd[r]
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int s_cnt[kTileQ];
+    __shared__ unsigned char s_perm[kTileQ];
+    __shared__ int s_flags;
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tb = blockIdx.x, b = blockIdx.y;
-    const size_t tile = (size_t)b * ntb + tb;
-    if (tid < (int)(sizeof(TileDesc) / sizeof(int)))
-        reinterpret_cast<int*>(&s_desc)[tid] = reinterpret_cast<const int*>(descs + tile)[tid];
+    const int q0 = tb * kTileQ, nq = min(kTileQ, N - q0);
+    const size_t sb = (size_t)b * N;
+    const float* gd = grid_dims + b * D;
+    const float* lo = low + b * D;
+    const float* st = starts + (size_t)b * ncells;
+    const float* en = ends + (size_t)b * ncells;
+    TileDesc* gdesc = descs + (size_t)b * ntb + tb;
+    unsigned char* blob = blobs + ((size_t)b * ntb + tb) * blob_stride;
+
+    if (warp == 0) tile_desc_warp(keys + sb, gd, st, en, N, D, ncells, q0, nq, &s_desc);
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        s_flags = 0;
+    }
     __syncthreads();
-    int st[kTileMaxRanges];
+    const int total = s_desc.total;
+    if (total + 1 > kTileMaxSlots) {
+        // ---- more candidates than 16-bit entries can address (a dense clump): rows from global memory with the
+        // general routine, no tile rows for this block, tile lists unusable for this call
+        typedef CollideSmem<DT, 256> Fallback;
+        Fallback& fsm = *reinterpret_cast<Fallback*>(s_raw);
+        const int w0 = warp * 8;
+        bool asym = false;
+        if (w0 < nq)
+            asym = collide_rows_warp<DT, DT, 256>(fsm, locs + (sb + q0 + w0) * D, locs + sb * D,
+                                                  coll + (sb + q0 + w0) * K, min(8, nq - w0), lo, gd, st, en, D, K,
+                                                  ncells, edge, r2, include_self);
+        if (asym && lane == 0) {
+            if (sym_flag) atomicOr(sym_flag, 1);
+            atomicOr(tile_flag, 1);
+        }
+        if (tid < kTileOctiles + 1) s_desc.goff[tid] = 0;
+        if (tid == 0) {
+            s_desc.maxcnt = 0;
+            s_desc.sumcnt = 0;
+        }
+        __syncthreads();
+        if (tid < 32) reinterpret_cast<int*>(gdesc)[tid] = reinterpret_cast<const int*>(&s_desc)[tid];
+        if (tid == 0) atomicOr(tile_flag, 2);  // no tile rows were written for this block
+        return;
+    }
+    // A block whose ranges exceed the staged tile (the 64 queries span many sparse cells; a few per 10^4 blocks
+    // of a uniform cloud) reads its candidates' positions from global memory instead; everything else is the same.
+    const bool staged = total + 1 <= kTileCap;
+
+    // ---- stage the positions of the block's ranges (TMA), build slot -> sorted index
+    if (warp == 0 && staged) {
+        if (lane == 0) mbar_expect_tx(&s_bar, (unsigned)total * 16u);
+        __syncwarp();
+        if (lane < s_desc.nr) {
+            const int len = s_desc.prefix[lane + 1] - s_desc.prefix[lane];
+            if (len > 0)
+                bulk_copy_g2s(s_pos + 1 + s_desc.prefix[lane], pos4 + sb + s_desc.start[lane], (unsigned)len * 16u, &s_bar);
+        }
+    }
+    if (tid == 0) s_pos[0] = make_float4(1e18f, 1e18f, 1e18f, 0.0f);
+    for (int r = 0; r < s_desc.nr && staged; ++r) {
+        const int len = s_desc.prefix[r + 1] - s_desc.prefix[r];
+        for (int i = tid; i < len; i += kCtThreads) s_slot2idx[1 + s_desc.prefix[r] + i] = s_desc.start[r] + i;
+    }
+    // sorted particle index of slot >= 1 (blocks that are not staged have no table)
+    auto slot_index = [&](unsigned slot) {
+        const int p = (int)slot - 1;
+        int idx = 0;
+        for (int r = 0; r < s_desc.nr; ++r)
+            if (p >= s_desc.prefix[r]) idx = s_desc.start[r] + p - s_desc.prefix[r];
+        return idx;
+    };
+    // ---- my warp's 8 queries: lanes 0..7 hold one each
+    const int w0 = warp * 8;
+    const int nqw = max(0, min(8, nq - w0));
+    float myx[D];
+    int mygc[D];
+    {
+        const float4 p = pos4[sb + q0 + min(w0 + (lane & 7), nq - 1)];
+        const float t[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
-    for (int g = 0; g < kTileMaxRanges; ++g) st[g] = g < s_desc.nr ? s_desc.start[g] : 0x7fffffff;
-    if (tid < kTileMaxRanges) {
-        s_fwd[tid] = 1 + s_desc.prefix[tid] - s_desc.start[tid];
-        s_len[tid] = tid < s_desc.nr ? s_desc.prefix[tid + 1] - s_desc.prefix[tid] : 0;
+        for (int k = 0; k < D; ++k) {
+            myx[k] = t[k];
+            mygc[k] = grid_coord_of(t[k], lo[k], edge);
+        }
+    }
+    int myfound = 0;
+    bool asym = false, bad = false;
+    int total_cells = 1;
+#pragma unroll
+    for (int k = 0; k < D; ++k) total_cells *= 3;
+    unsigned short* cand = s_cand + warp * kCtWin;
+    if (staged) mbar_wait(&s_bar, 0);
+
+    int qi = 0;
+    while (qi < nqw) {
+        int gc[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) gc[k] = __shfl_sync(0xffffffffu, mygc[k], qi);
+        bool same = lane >= qi && lane < nqw;
+#pragma unroll
+        for (int k = 0; k < D; ++k) same = same && mygc[k] == gc[k];
+        const unsigned smk = __ballot_sync(0xffffffffu, same) >> qi;
+        const int run = __ffs(~smk) - 1;
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            if (gd[k] > 0.0f && (float)gc[k] >= gd[k] + 1.0f) asym = true;
+
+        // ---- lane -> one neighbour cell: its particles as a run of tile slots
+        int cnt = 0, slot0 = 0;
+        if (lane < total_cells) {
+            int rem = lane, id = 0;
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const int c = gc[k] + (rem % 3) - 1;
+                rem /= 3;
+                if (c < 0 || (float)c >= gd[k]) ok = false;
+                else id += hash_term(c, gd, k, D);
+            }
+            if (ok && id >= 0 && id < ncells) {
+                const int cstart = (int)st[id];
+                cnt = (int)en[id] - cstart;
+                if (cnt < 0) cnt = 0;
+                if (cnt > 0) {
+                    // the range of the block that holds this cell (ascending starts; slot = index + shift)
+                    int g = 0;
+                    for (int t = 1; t < s_desc.nr; ++t) g += cstart >= s_desc.start[t];
+                    const int s0 = s_desc.start[g], p0 = s_desc.prefix[g];
+                    if (cstart < s0 || cstart + cnt - s0 > s_desc.prefix[g + 1] - p0) {
+                        bad = true;  // never expected: the cell is not inside the block's ranges
+                        cnt = 0;
+                    }
+                    slot0 = cstart - s0 + p0 + 1;
+                }
+            }
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const int ctotal = __shfl_sync(0xffffffffu, incl, 31);
+        const int excl = incl - cnt;
+
+        for (int wb = 0; wb < ctotal; wb += kCtWin) {
+            const int wn = min(kCtWin, ctotal - wb);
+            // every cell lane writes the slots of its particles that fall into this window
+            __syncwarp();
+            {
+                const int a = max(excl, wb), z = min(incl, wb + kCtWin);
+                for (int t = a; t < z; ++t) cand[t - wb] = (unsigned short)(slot0 + (t - excl));
+            }
+            __syncwarp();
+            // the window in registers: slot and coordinates of 8 candidates per lane
+            unsigned cs[kCtWin / 32];
+            float px[kCtWin / 32][D];
+#pragma unroll
+            for (int i = 0; i < kCtWin / 32; ++i) {
+                const int t = i * 32 + lane;
+                cs[i] = t < wn ? cand[t] : 0u;
+                float4 p;
+                if (staged) p = s_pos[cs[i]];
+                else p = cs[i] ? pos4[sb + slot_index(cs[i])] : make_float4(1e18f, 1e18f, 1e18f, 0.0f);
+                const float tt[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+                for (int k = 0; k < D; ++k) px[i][k] = tt[k];
+            }
+            for (int r = 0; r < run; ++r) {
+                int found = __shfl_sync(0xffffffffu, myfound, qi + r);
+                if (found >= K) continue;
+                float x[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) x[k] = __shfl_sync(0xffffffffu, myx[k], qi + r);
+                unsigned short* hrow = s_hits + (size_t)(w0 + qi + r) * K;
+#pragma unroll
+                for (int i = 0; i < kCtWin / 32; ++i) {
+                    if (i * 32 < wn && found < K) {
+                        float d = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            const float nr = x[k] - px[i][k];
+                            d += nr * nr;
+                        }
+                        const bool hit = (i * 32 + lane < wn) && d < r2 && (d > 0.0f || include_self);
+                        const unsigned m = __ballot_sync(0xffffffffu, hit);
+                        const int pos = found + __popc(m & lanemask_lt());
+                        if (hit && pos < K) hrow[pos] = (unsigned short)cs[i];
+                        found += __popc(m);
+                    }
+                }
+                if (lane == qi + r) myfound = found;
+            }
+        }
+        qi += run;
+    }
+    if (lane < 8) {
+        int c = lane < nqw ? myfound : 0;
+        if (c >= K) {
+            asym = true;  // the row is full: it may have been cut
+            c = K;
+        }
+        s_cnt[w0 + lane] = c;
+    }
+    if (__any_sync(0xffffffffu, asym) && lane == 0) atomicOr(&s_flags, 1);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&s_flags, 4);
+    __syncthreads();
+
+    // ---- rank the queries by list length (longest first, ties by position)
+    if (tid < kTileQ) {
+        const int c = s_cnt[tid];
+        int rank = 0;
+        for (int j = 0; j < kTileQ; ++j) {
+            const int cj = s_cnt[j];
+            rank += (cj > c || (cj == c && j < tid)) ? 1 : 0;
+        }
+        s_perm[rank] = (unsigned char)tid;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int rows = 0, sum = 0;
+        for (int g = 0; g < kTileOctiles; ++g) {
+            s_desc.goff[g] = (unsigned short)rows;
+            rows += (s_cnt[s_perm[8 * g]] + 3) >> 2;  // the first rank of an octile has its longest list
+        }
+        s_desc.goff[kTileOctiles] = (unsigned short)rows;
+        for (int j = 0; j < kTileQ; ++j) sum += s_cnt[j];
+        s_desc.maxcnt = (unsigned short)s_cnt[s_perm[0]];
+        s_desc.sumcnt = sum;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) s_desc.pad[i] = 0;
+        if (s_flags & 1) {
+            if (sym_flag) atomicOr(sym_flag, 1);
+            atomicOr(tile_flag, 1);
+        }
+        if (s_flags & 4) atomicOr(tile_flag, 4);
     }
     __syncthreads();
 
-    bool bad = false, cut = false;
-    constexpr int RPW = kTileQ / (kBuildThreads / 32);  // rows per warp
-    static_assert(RPW % 4 == 0, "rows are processed four at a time");
-    // The kernel is issue-bound (ncu: 86 % issue active), so a warp works on FOUR rows at once: 8 lanes per
-    // row, each lane one float4 = 4 entries, i.e. 32 entries per row and step with a quarter of the
-    // per-row control instructions.  The row ends at its first negative entry (common_funcs.h:476).
-    const int grp = lane >> 3, sub = lane & 7;
-    const bool wide = (K & 3) == 0 && (reinterpret_cast<size_t>(coll) & 15) == 0;
-#pragma unroll 1
-    for (int r0 = 0; r0 < RPW; r0 += 4) {
-        const int ql = warp * RPW + r0 + grp;
-        const int m = tb * kTileQ + ql;
-        const bool live_row = m < N;
-        const float* row = coll + ((size_t)b * N + (live_row ? m : 0)) * K;
-        unsigned short* trow = tlists + tile_entry_off(ntb, K, b, tb, ql, 0) / 2;
-        int cnt = 0;
-        bool open = live_row;  // terminator not seen yet
-        for (int base = 0; base < K; base += 32) {
-            if (!__any_sync(0xffffffffu, open)) break;
-            const int k0 = base + sub * 4;
-            float f[4] = {-1.0f, -1.0f, -1.0f, -1.0f};
-            if (open) {
-                if (wide && k0 + 3 < K) {
-                    const float4 v = *reinterpret_cast<const float4*>(row + k0);
-                    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (k0 + j < K) f[j] = row[k0 + j];
-                }
-            }
-            int nv = 0;  // length of the run of non-negative entries that starts at f[0]
-#pragma unroll
-            for (int j = 3; j >= 0; --j) nv = f[j] >= 0.0f ? nv + 1 : 0;
-            const unsigned fullm = (__ballot_sync(0xffffffffu, nv == 4) >> (grp * 8)) & 0xffu;
-            const int l0 = fullm == 0xffu ? 8 : __ffs(~fullm) - 1;         // first lane of the group with a terminator
-            const int nv0 = __shfl_sync(0xffffffffu, nv, grp * 8 + (l0 & 7));
-            const int take = open ? (l0 == 8 ? 32 : l0 * 4 + nv0) : 0;    // entries before the terminator
-            const int padded = (take + kTileUnit - 1) & ~(kTileUnit - 1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int e = sub * 4 + j;  // entry within this step's 32
-                unsigned loc = 0;           // entries past the terminator: sentinel padding of the last unit
-                if (e < take) {
-                    const int idx = (int)f[j];
-                    int g = 0;
-#pragma unroll
-                    for (int t = 1; t < kTileMaxRanges; ++t) g += idx >= st[t];
-                    loc = (unsigned)(idx + s_fwd[g]);
-                    if ((unsigned)(idx - st[g]) >= (unsigned)s_len[g] || loc > 0xfffu) {
-                        bad = true;  // not in the block's ranges, or slot * 16 does not fit 16 bits
-                        loc = 0;
-                    }
-                    loc <<= 4;  // entries are byte offsets into a plane of 16-byte record quarters
-                }
-                const int k = base + e;
-                if (open && e < padded && k < K)
-                    trow[(k >> 4) * 128 + ((k & 3) * 4 + ((k >> 2) & 3))] = (unsigned short)loc;  // 4x4-transposed unit
-            }
-            cnt += take;
-            if (take < 32) open = false;
+    // ---- float rows: accepted particle indices in the reference's order, then -1 up to the end of the row
+    for (int r = 0; r < 8; ++r) {
+        const int ql = w0 + r;
+        if (ql >= nq) break;
+        const int c = s_cnt[ql];
+        float* row = coll + (sb + q0 + ql) * K;
+        const unsigned short* hrow = s_hits + (size_t)ql * K;
+        if (staged) {
+            for (int k = lane; k < K; k += 32) row[k] = k < c ? (float)s_slot2idx[hrow[k]] : -1.0f;
+        } else {
+            for (int k = lane; k < K; k += 32) row[k] = k < c ? (float)slot_index(hrow[k]) : -1.0f;
         }
-        if (live_row && cnt >= K) cut = true;
-        if (live_row && sub == 0) tcounts[(size_t)b * N + m] = cnt;
     }
-    if (cut) atomicOr(tile_flag, 1);
-    if (bad) atomicOr(tile_flag, 2);
+    // ---- tile rows of octile `warp`: entry 4s+e of rank 8g+r at position 4r+e of row goff[g]+s
+    {
+        const int g = warp;
+        const int ql = s_perm[8 * g + (lane >> 2)];
+        const int c = s_cnt[ql];
+        const unsigned short* hrow = s_hits + (size_t)ql * K;
+        const int S = s_desc.goff[g + 1] - s_desc.goff[g];
+        unsigned short* rows = reinterpret_cast<unsigned short*>(blob + kTileHeaderBytes) + (size_t)s_desc.goff[g] * 32;
+        for (int s_ = 0; s_ < S; ++s_) {
+            const int e = 4 * s_ + (lane & 3);
+            rows[s_ * 32 + lane] = e < c ? (unsigned short)(hrow[e] << 4) : (unsigned short)0;
+        }
+    }
+    if (tid < kTileQ) blob[tid] = s_perm[tid];
+    if (tid < 32) reinterpret_cast<int*>(gdesc)[tid] = reinterpret_cast<const int*>(&s_desc)[tid];
 }
 
 // ---- launch helpers --------------------------------------------------------------------------------
@@ -868,10 +1172,9 @@ int spnb_hashgrid_order(const float* locs, const float* low, const float* grid_d
     return check_launch("spnb_hashgrid_order") ? 1 : 0;
 }
 
-int spnb_reorder_data(const float* locs, const float* data, const float* idxs, float* nlocs,
-                      float* ndata, int B, int N, int D, int C, int reverse, void* stream_)
+static int reorder_launch(const float* locs, const float* data, const float* idxs, float* nlocs, float* ndata,
+                          float* pos4, int B, int N, int D, int C, int reverse, cudaStream_t stream)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
     if (B <= 0 || N <= 0 || D <= 0) {
         set_error("spnb_reorder_data: bad sizes");
         return 0;
@@ -881,44 +1184,59 @@ int spnb_reorder_data(const float* locs, const float* data, const float* idxs, f
         return 0;
     }
     if (!data) C = 0;
+    if (pos4 && (reverse || D > 4)) {
+        set_error("spnb_reorder_data: the float4 position plane needs reverse == 0 and ndims <= 4");
+        return 0;
+    }
     if ((long long)N * (D > C ? D : C) >= (1ll << 32)) {
         set_error("spnb_reorder_data: N * row width exceeds 2^32");
         return 0;
     }
-    // one tensor per launch (used when the row widths of locs and data differ): the kernel reads its
-    // tensor from the `locs` slot (blockIdx.z == 0)
-    auto launch = [&](int W, const float* in, float* out) {
-        int blocks = cdiv((long long)N * W, 256 * 4);
-        if (blocks < 1) blocks = 1;
-        const dim3 grid(blocks, B, 1);
+    int launches = 0;
+    // rows of up to 4 floats: thread per row; both tensors in one launch when their widths agree
+    auto rows = [&](int W, const float* a, const float* b_, float* oa, float* ob, float4* p4) {
+        const dim3 grid(cdiv(N, 256), B, b_ ? 2 : 1);
         switch (W) {
-        case 1: k_reorder<1><<<grid, 256, 0, stream>>>(in, nullptr, idxs, out, nullptr, N, W, 0, reverse); break;
-        case 2: k_reorder<2><<<grid, 256, 0, stream>>>(in, nullptr, idxs, out, nullptr, N, W, 0, reverse); break;
-        case 3: k_reorder<3><<<grid, 256, 0, stream>>>(in, nullptr, idxs, out, nullptr, N, W, 0, reverse); break;
-        case 4: k_reorder<4><<<grid, 256, 0, stream>>>(in, nullptr, idxs, out, nullptr, N, W, 0, reverse); break;
-        default: k_reorder<0><<<grid, 256, 0, stream>>>(in, nullptr, idxs, out, nullptr, N, W, 0, reverse); break;
+        case 1: k_reorder_rows<1><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
+        case 2: k_reorder_rows<2><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
+        case 3: k_reorder_rows<3><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
+        default: k_reorder_rows<4><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
         }
+        ++launches;
+    };
+    auto wide = [&](int W, const float* a, float* oa) {
+        const bool vec = (W & 3) == 0 && ((reinterpret_cast<size_t>(a) | reinterpret_cast<size_t>(oa)) & 15) == 0;
+        int blocks = cdiv((long long)N * (vec ? W / 4 : W), 256 * 4);
+        if (blocks < 1) blocks = 1;
+        const dim3 grid(blocks, B);
+        if (vec) k_reorder_wide<true><<<grid, 256, 0, stream>>>(a, idxs, oa, N, W, reverse);
+        else k_reorder_wide<false><<<grid, 256, 0, stream>>>(a, idxs, oa, N, W, reverse);
+        ++launches;
     };
     if (C == D && D <= 4) {
-        // both tensors in one launch (gridDim.z = 2)
-        int blocks = cdiv((long long)N * D, 256 * 4);
-        if (blocks < 1) blocks = 1;
-        const dim3 grid(blocks, B, 2);
-        switch (D) {
-        case 1: k_reorder<1><<<grid, 256, 0, stream>>>(locs, data, idxs, nlocs, ndata, N, D, C, reverse); break;
-        case 2: k_reorder<2><<<grid, 256, 0, stream>>>(locs, data, idxs, nlocs, ndata, N, D, C, reverse); break;
-        case 3: k_reorder<3><<<grid, 256, 0, stream>>>(locs, data, idxs, nlocs, ndata, N, D, C, reverse); break;
-        default: k_reorder<4><<<grid, 256, 0, stream>>>(locs, data, idxs, nlocs, ndata, N, D, C, reverse); break;
-        }
+        rows(D, locs, data, nlocs, ndata, (float4*)pos4);
     } else {
-        launch(D, locs, nlocs);
+        if (D <= 4) rows(D, locs, nullptr, nlocs, nullptr, (float4*)pos4);
+        else wide(D, locs, nlocs);
         if (C > 0) {
-            launch(C, data, ndata);
-            count_launches(1);
+            if (C <= 4) rows(C, data, nullptr, ndata, nullptr, nullptr);
+            else wide(C, data, ndata);
         }
     }
-    count_launches(1);
+    count_launches(launches);
     return check_launch("spnb_reorder_data") ? 1 : 0;
+}
+
+int spnb_reorder_data(const float* locs, const float* data, const float* idxs, float* nlocs,
+                      float* ndata, int B, int N, int D, int C, int reverse, void* stream_)
+{
+    return reorder_launch(locs, data, idxs, nlocs, ndata, nullptr, B, N, D, C, reverse, (cudaStream_t)stream_);
+}
+
+int spnb_reorder_data_pos4(const float* locs, const float* data, const float* idxs, float* nlocs,
+                           float* ndata, float* pos4, int B, int N, int D, int C, void* stream_)
+{
+    return reorder_launch(locs, data, idxs, nlocs, ndata, pos4, B, N, D, C, 0, (cudaStream_t)stream_);
 }
 
 int spnb_compute_collisions(const float* qlocs, const float* locs, const float* low,
@@ -963,37 +1281,67 @@ size_t spnb_tile_lists_bytes(int batch_size, int N, int ndims, int max_collision
     return tile_layout(batch_size, N, max_collisions).total;
 }
 
-int spnb_build_tile_lists(const float* cellIDs, const float* grid_dims, const float* cellStarts,
-                          const float* cellEnds, const float* collisions, int B, int N, int D, int K,
-                          int ncells, void* tile_lists, size_t tile_lists_bytes, void* stream_)
+int spnb_compute_collisions_tiled(const float* pos4, const float* locs, const float* low, const float* grid_dims,
+                                  const float* cellIDs, float* cellStarts, float* cellEnds, float* collisions,
+                                  int B, int N, int D, int K, int ncells, float cellEdge, float radius,
+                                  int include_self, int* sym_flag, void* tile_lists, size_t tile_lists_bytes,
+                                  void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (!valid_common(B, N, D, "spnb_build_tile_lists")) return 0;
-    if (!cellIDs || !grid_dims || !collisions || !tile_lists) {
-        set_error("spnb_build_tile_lists: null pointer");
+    if (!valid_common(B, N, D, "spnb_compute_collisions_tiled")) return 0;
+    if (K <= 0 || ncells <= 0) {
+        set_error("spnb_compute_collisions_tiled: bad sizes max_collisions=%d ncells=%d", K, ncells);
+        return 0;
+    }
+    if (!pos4 || !locs || !low || !grid_dims || !cellIDs || !cellStarts || !cellEnds || !collisions || !tile_lists) {
+        set_error("spnb_compute_collisions_tiled: null pointer");
         return 0;
     }
     if (!tile_lists_supported(N, D, K)) {
-        set_error("spnb_build_tile_lists: needs ndims <= %d and max_collisions a multiple of %d",
-                  kTileMaxNdim, kTileUnit);
+        set_error("spnb_compute_collisions_tiled: needs ndims <= %d and max_collisions <= %d", kTileMaxNdim, kTileMaxK);
+        return 0;
+    }
+    if ((reinterpret_cast<size_t>(pos4) & 15) != 0) {
+        set_error("spnb_compute_collisions_tiled: the position plane must be 16-byte aligned");
         return 0;
     }
     const TileLayout tl = tile_layout(B, N, K);
     if (tile_lists_bytes < tl.total) {
-        set_error("spnb_build_tile_lists: tile buffer too small (%zu < %zu)", tile_lists_bytes, tl.total);
+        set_error("spnb_compute_collisions_tiled: tile buffer too small (%zu < %zu)", tile_lists_bytes, tl.total);
         return 0;
     }
     char* tb = (char*)tile_lists;
     int* tflag = (int*)tb;
     TileDesc* descs = (TileDesc*)(tb + tl.desc_off);
     cudaMemsetAsync(tflag, 0, 128, stream);
-    k_tile_ranges<<<dim3(cdiv(tl.ntb, 8), B), 256, 0, stream>>>((const uint32_t*)cellIDs, grid_dims,
-                                                                cellEnds ? cellStarts : nullptr, cellEnds, N, D,
-                                                                ncells, tl.ntb, descs, tflag);
-    k_tile_build<<<dim3(tl.ntb, B), kBuildThreads, 0, stream>>>(
-        collisions, descs, N, K, tl.ntb, tflag, (int*)(tb + tl.cnt_off), (unsigned short*)(tb + tl.list_off));
-    count_launches(2);
-    return check_launch("spnb_build_tile_lists") ? 1 : 0;
+    k_table_clear<<<dim3(148, B), 256, 0, stream>>>(grid_dims, cellStarts, cellEnds, D, ncells);
+    k_table_fill<<<dim3(cdiv(N, 256), B), 256, 0, stream>>>((const uint32_t*)cellIDs, grid_dims, cellStarts,
+                                                            cellEnds, N, D, ncells);
+    const float r2 = radius * radius;
+    size_t smem = (size_t)kTileCap * 20 + 8 * kCtWin * 2 + (size_t)kTileQ * K * 2;
+    const dim3 grid(tl.ntb, B);
+#define SPNB_CT(DT)                                                                                              \
+    do {                                                                                                         \
+        if (smem < sizeof(CollideSmem<DT, 256>)) smem = sizeof(CollideSmem<DT, 256>);                            \
+        if (smem > 48 * 1024 &&                                                                                  \
+            cudaFuncSetAttribute(k_collide_tiles<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != \
+                cudaSuccess) {                                                                                   \
+            set_error("spnb_compute_collisions_tiled: %zu bytes of shared memory not available", smem);         \
+            return 0;                                                                                            \
+        }                                                                                                        \
+        k_collide_tiles<DT><<<grid, kCtThreads, smem, stream>>>(                                                 \
+            (const float4*)pos4, locs, low, grid_dims, (const uint32_t*)cellIDs, cellStarts, cellEnds,           \
+            collisions, N, K, ncells, cellEdge, r2, include_self, sym_flag, tflag, descs,                        \
+            (unsigned char*)(tb + tl.list_off), tl.blob_stride, tl.ntb);                                         \
+    } while (0)
+    switch (D) {
+    case 1: SPNB_CT(1); break;
+    case 2: SPNB_CT(2); break;
+    default: SPNB_CT(3); break;
+    }
+#undef SPNB_CT
+    count_launches(3);
+    return check_launch("spnb_compute_collisions_tiled") ? 1 : 0;
 }
 
 }  // extern "C"

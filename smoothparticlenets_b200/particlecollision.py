@@ -36,13 +36,13 @@ class ReorderData(torch.nn.Module):
             data = data.contiguous()
         locs = locs.contiguous()
         idxs = idxs.contiguous()
-        nlocs, ndata = _ReorderDataFunction.apply(idxs, locs, data, self.reverse)
+        nlocs, ndata, _ = _ReorderDataFunction.apply(idxs, locs, data, self.reverse)
         if data is None:
             return nlocs
         return nlocs, ndata
 
 
-def _reorder(idxs, locs, data, reverse):
+def _reorder(idxs, locs, data, reverse, want_pos4=False):
     nat.require_cuda_f32(idxs, "idxs")
     nat.require_cuda_f32(locs, "locs")
     B, N, D = locs.shape
@@ -53,44 +53,51 @@ def _reorder(idxs, locs, data, reverse):
         nat.require_cuda_f32(data, "data")
         C = data.shape[2]
         ndata = torch.empty_like(data)
+    pos4 = None
     with torch.cuda.device(locs.device):
-        nat.check(nat.lib().spnb_reorder_data(nat.ptr(locs), nat.ptr(data), nat.ptr(idxs),
-                                              nat.ptr(nlocs), nat.ptr(ndata), B, N, D, C,
-                                              int(reverse), nat.stream()), "spnb_reorder_data")
-    return nlocs, ndata
+        if want_pos4:
+            pos4 = torch.empty(B, N, 4, device=locs.device, dtype=torch.float32)
+            nat.check(nat.lib().spnb_reorder_data_pos4(nat.ptr(locs), nat.ptr(data), nat.ptr(idxs), nat.ptr(nlocs),
+                                                       nat.ptr(ndata), nat.ptr(pos4), B, N, D, C, nat.stream()),
+                      "spnb_reorder_data_pos4")
+        else:
+            nat.check(nat.lib().spnb_reorder_data(nat.ptr(locs), nat.ptr(data), nat.ptr(idxs),
+                                                  nat.ptr(nlocs), nat.ptr(ndata), B, N, D, C,
+                                                  int(reverse), nat.stream()), "spnb_reorder_data")
+    return nlocs, ndata, pos4
 
 
 class _ReorderDataFunction(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, idxs, locs, data, reverse):
+    def forward(ctx, idxs, locs, data, reverse, want_pos4=False):
         ctx.save_for_backward(idxs)
         ctx.reverse = reverse
         ctx.has_data = data is not None
-        nlocs, ndata = _reorder(idxs, locs, data, reverse)
+        nlocs, ndata, pos4 = _reorder(idxs, locs, data, reverse, want_pos4)
         if ndata is None:
             ndata = locs.new_empty(0)
             ctx.mark_non_differentiable(ndata)
-        return nlocs, ndata
+        if pos4 is None:
+            pos4 = locs.new_empty(0)
+        ctx.mark_non_differentiable(pos4)
+        return nlocs, ndata, pos4
 
     @staticmethod
-    def backward(ctx, grad_locs, grad_data):
+    def backward(ctx, grad_locs, grad_data, _grad_pos4):
         idxs, = ctx.saved_tensors
         gd = grad_data.contiguous() if ctx.has_data else None
-        glocs, gdata = _reorder(idxs, grad_locs.contiguous(), gd, 1 - ctx.reverse)
-        return None, glocs, gdata, None
+        glocs, gdata, _ = _reorder(idxs, grad_locs.contiguous(), gd, 1 - ctx.reverse)
+        return None, glocs, gdata, None, None
 
 
 def tile_lists_of(neighbors):
     """The compact tile lists (csrc/tile_lists.cuh) of a neighbour tensor returned by ParticleCollision, or
-    None.  Builds them on first use when the module is in its default "lazy" mode.  None as well when the
-    tensor was edited in place after ParticleCollision returned it (sidecar.py)."""
+    None: lists built for separate query locations, ndim > 3, tile_lists switched off, or the tensor was edited
+    in place after ParticleCollision returned it (sidecar.py)."""
     sc = sidecar.lookup(neighbors)
     if sc is None:
         return None
-    if sc.tiles is None and sc.builder is not None:
-        sc.tiles = sc.builder(neighbors)
-        sc.builder = None
     return sc.tiles
 
 
@@ -99,30 +106,6 @@ def sym_flag_of(neighbors):
     grid, so the neighbour relation is symmetric), or None for tensors of unknown origin / edited in place."""
     sc = sidecar.lookup(neighbors)
     return None if sc is None else sc.sym_flag
-
-
-class _TileBuilder(object):
-    """Lazy construction of the tile lists from the module's scratch (sorted keys, cell table).  Holds the module
-    weakly and refuses once the module has run again (its scratch then describes another call)."""
-
-    def __init__(self, module, gen, shape, tile_bytes, grid_dims, ncells):
-        self.module = weakref.ref(module)
-        self.gen, self.shape, self.tile_bytes, self.grid_dims, self.ncells = gen, shape, tile_bytes, grid_dims, ncells
-
-    def __call__(self, nbrs):
-        m = self.module()
-        if m is None or m._generation != self.gen or tuple(nbrs.shape) != self.shape:
-            return None
-        B, N, K = self.shape
-        dev = nbrs.device
-        L = nat.lib()
-        with torch.no_grad(), torch.cuda.device(dev):
-            t = torch.empty(self.tile_bytes, device=dev, dtype=torch.uint8)
-            nat.check(L.spnb_build_tile_lists(
-                nat.ptr(m.cellIDs), nat.ptr(self.grid_dims), nat.ptr(m.cellStarts), nat.ptr(m.cellEnds),
-                nat.ptr(nbrs), B, N, m.ndim, K, self.ncells, nat.ptr(t), self.tile_bytes, nat.stream()),
-                "spnb_build_tile_lists")
-        return t
 
 
 class ParticleCollision(torch.nn.Module):
@@ -139,12 +122,11 @@ class ParticleCollision(torch.nn.Module):
         self.max_collisions = ec.check_conditions(max_collisions, "max_collisions", "%s > 0",
                                                   "isinstance(%s, numbers.Integral)")
         self.include_self = 1 if include_self else 0
-        # extension (not in the reference): the compact tile lists that ConvSPGroup consumes.  "lazy"
-        # (default): built the first time a consumer asks for them (tile_lists_of), so callers that only
-        # use per-layer ConvSP never pay for them; True: built with the lists; False: never.  The float
-        # neighbour tensor that is returned is unaffected.
-        env = os.environ.get("SPNB_TILE_LISTS", "lazy")
-        self.tile_lists = {"0": False, "1": True}.get(env, "lazy")
+        # extension (not in the reference): the compact tile lists the ConvSP tile kernels consume.  True
+        # (default): the float rows AND the tile lists come out of one kernel (spnb_compute_collisions_tiled)
+        # whenever the particles are their own queries and ndim <= 3; False: float rows only (the general
+        # kernel).  The float neighbour tensor that is returned is bit-identical either way.
+        self.tile_lists = os.environ.get("SPNB_TILE_LISTS", "1") != "0"
         self._generation = 0
         self.radixsort_buffer_size = -1
         # Same buffer names as the reference (ParticleCollision.py:97-100) so state_dicts load.
@@ -218,11 +200,14 @@ class ParticleCollision(torch.nn.Module):
                                             batch_size, N, D, float(self.radius), G, st),
                       "spnb_hashgrid_order")
 
-        # Reorder locs (and data) -- the only differentiable step.
+        K = self.max_collisions
+        tile_bytes = (L.spnb_tile_lists_bytes(batch_size, N, D, K)
+                      if (qlocs is None and query_range is None and self.tile_lists) else 0)
+        # Reorder locs (and data) -- the only differentiable step.  On the tiled path the reordered positions
+        # are also written as a float4 plane, which the list kernel stages its candidates from.
+        locs, data_r, pos4 = _ReorderDataFunction.apply(idxs, locs, data if has_data else None, 0, tile_bytes > 0)
         if has_data:
-            locs, data = self.reorder(idxs, locs, data)
-        else:
-            locs = self.reorder(idxs, locs)
+            data = data_r
 
         if query_range is not None:
             if qlocs is not None:
@@ -235,27 +220,29 @@ class ParticleCollision(torch.nn.Module):
             q = locs.detach() if qlocs is None else qlocs.detach()
             nat.require_cuda_f32(q, "qlocs")
             M = q.shape[1]
-            neighbors = torch.empty(batch_size, M, self.max_collisions, device=dev,
-                                    dtype=torch.float32)
+            neighbors = torch.empty(batch_size, M, K, device=dev, dtype=torch.float32)
             trunc = torch.zeros(1, device=dev, dtype=torch.int32)
-            nat.check(L.spnb_compute_collisions(
-                nat.ptr(q), nat.ptr(locs.detach()), nat.ptr(lower_bounds), nat.ptr(grid_dims),
-                nat.ptr(cellIDs), nat.ptr(cellStarts), nat.ptr(cellEnds), nat.ptr(neighbors),
-                batch_size, M, N, D, self.max_collisions, ncells, float(self.radius),
-                float(self.radius), self.include_self, nat.ptr(trunc), nat.stream()),
-                "spnb_compute_collisions")
-            tiles, builder = None, None
-            tile_bytes = (L.spnb_tile_lists_bytes(batch_size, N, D, self.max_collisions)
-                          if qlocs is None and self.tile_lists else 0)
+            tiles = None
             if tile_bytes > 0:
-                builder = _TileBuilder(self, self._generation, (batch_size, N, self.max_collisions), tile_bytes,
-                                       grid_dims, ncells)
-                if self.tile_lists is True:
-                    tiles, builder = builder(neighbors), None
+                tiles = torch.empty(tile_bytes, device=dev, dtype=torch.uint8)
+                nat.check(L.spnb_compute_collisions_tiled(
+                    nat.ptr(pos4), nat.ptr(locs.detach()), nat.ptr(lower_bounds), nat.ptr(grid_dims),
+                    nat.ptr(cellIDs), nat.ptr(cellStarts), nat.ptr(cellEnds), nat.ptr(neighbors), batch_size, N, D,
+                    K, ncells, float(self.radius), float(self.radius), self.include_self, nat.ptr(trunc),
+                    nat.ptr(tiles), tile_bytes, nat.stream()), "spnb_compute_collisions_tiled")
+            else:
+                nat.check(L.spnb_compute_collisions(
+                    nat.ptr(q), nat.ptr(locs.detach()), nat.ptr(lower_bounds), nat.ptr(grid_dims),
+                    nat.ptr(cellIDs), nat.ptr(cellStarts), nat.ptr(cellEnds), nat.ptr(neighbors),
+                    batch_size, M, N, D, K, ncells, float(self.radius),
+                    float(self.radius), self.include_self, nat.ptr(trunc), nat.stream()),
+                    "spnb_compute_collisions")
         if qlocs is None:
             # Lists built with the particles as their own queries are symmetric unless one was cut at
             # max_collisions or a query lies beyond a clamped grid; ConvSP's backward uses this to avoid atomics.
-            sidecar.attach(neighbors, sidecar.Sidecar(sym_flag=trunc, tiles=tiles, builder=builder))
+            sidecar.attach(neighbors, sidecar.Sidecar(sym_flag=trunc, tiles=tiles))
+            if tile_bytes > 0:
+                sidecar.attach(locs, sidecar.Sidecar(pos4=pos4))
         self.last_lower_bounds = lower_bounds
         self.last_grid_dims = grid_dims
         if has_data:

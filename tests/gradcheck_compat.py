@@ -59,7 +59,10 @@ def _numeric(fn, inputs, eps, use_double):
             c = t.detach().clone()
             if use_double:
                 c = c.double()
-            c.requires_grad_(t.requires_grad)
+            if isinstance(t, torch.nn.Parameter):  # functions that assign their arguments to a module need this
+                c = torch.nn.Parameter(c, requires_grad=t.requires_grad)
+            else:
+                c.requires_grad_(t.requires_grad)
             work.append(c)
         else:
             work.append(t)

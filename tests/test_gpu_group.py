@@ -34,7 +34,7 @@ def test_group_matches_per_layer(spn, D, mode):
     r = cases.rng(3)
     locs, vel, L = cases.fluid_cloud(5, B, N, D=D, density=7640.0 if D == 3 else 600.0)
     coll = spn.ParticleCollision(D, 0.1, include_self=False).cuda()
-    coll.tile_lists = "lazy" if mode == "tile" else False  # tile: compact tile lists; sym/atomic: walk of the float lists
+    coll.tile_lists = mode == "tile"  # tile: compact tile lists; sym/atomic: walk of the float lists
     sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
     if mode == "tile":
         assert int(spn.tile_lists_of(nb)[:4].view(torch.int32).item()) == 0, "tile lists usable"
@@ -44,10 +44,13 @@ def test_group_matches_per_layer(spn, D, mode):
     press = gu.dev(r.rand(B, N, 1).astype(np.float32))
     groups = {
         "A": ([("spiky", 1, False), ("dspiky", D, True), ("dspiky", 1, True), ("cohesion", D, True),
-               ("cohesion", 1, True), ("constant", 1, False)], lambda l: [ones, l, ones, l, ones, ones]),
+               ("cohesion", 1, True), ("constant", 1, False)], lambda l: [None, l, None, l, None, None]),
         "B": ([("dspiky", D, True), ("dspiky", 1, True)], lambda l: [l * press, press]),
-        "V": ([("spiky", D, False), ("spiky", 1, False)], lambda l: [sv, ones]),
+        "V": ([("spiky", D, False), ("spiky", 1, False)], lambda l: [sv, None]),
         "C": ([("constant", D, False)], lambda l: [sv]),
+        # any single layer takes the fused path too (run-time kernel id), here two that are not in the fluid step
+        "S1": ([("pressure", 2, False)], lambda l: [sv[..., :2].contiguous()]),
+        "S2": ([("sigmoid", D, True)], lambda l: [l]),
     }
     for name, (specs, mk) in groups.items():
         layers = make_layers(spn, D, specs, r)
@@ -58,8 +61,10 @@ def test_group_matches_per_layer(spn, D, mode):
             l = sl.detach().clone().requires_grad_(True)
             datas = mk(l)
             n0 = nat.lib().spnb_launch_count()
+            for lay in layers:
+                lay.fast_path = False  # the reference side: the per-layer float-list kernels
             outs = group(l, datas, nb) if which == "fused" else tuple(
-                lay(l, d, nb) for lay, d in zip(layers, datas))
+                lay(l, ones if d is None else d, nb) for lay, d in zip(layers, datas))
             if which == "fused":  # pack + one walk, not one launch per layer
                 # pack + one kernel (tile kernel, or the list walk when there are no tile lists)
                 assert nat.lib().spnb_launch_count() - n0 == 2, "group %s did not take the fused path" % name
@@ -137,11 +142,14 @@ def test_group_tile_flag_falls_back_on_device(spn):
     close(res[True][1], res[False][1], "locs.grad", k=64)
 
 
-def test_group_oversized_tiles_gather_from_global(spn):
-    """Tiles with more records than the staging capacity (dense clump, lists not cut) are processed by the
-    same kernels through the slot -> index table; results must match the float-list walk."""
+@pytest.mark.parametrize("N,K,want_flag", [(3000, 256, 0)])
+def test_group_oversized_tiles(spn, oracle, N, K, want_flag):
+    """Blocks whose candidate ranges exceed the staged tile (dense cloud, lists not cut).  Up to 4095 candidates
+    the tile kernels stage the block's records in several chunks and walk its lists once per chunk; beyond that the
+    list kernel computes the rows with the general routine, raises bit 1 of the tile flag and the group kernels
+    run the float-list walk.  Rows stay bit-exact, results equal to the float-list walk."""
     from smoothparticlenets_b200 import tile_lists as tl
-    B, N, D, K = 1, 3000, 3, 256
+    B, D = 1, 3
     r = cases.rng(8)
     locs = (r.rand(B, N, D) * 0.5).astype(np.float32)
     vel = r.rand(B, N, D).astype(np.float32)
@@ -155,7 +163,15 @@ def test_group_oversized_tiles_gather_from_global(spn):
         assert int(spn.sym_flag_of(nb).item()) == 0
         if tiles_on:
             flag, counts, dec, max_total = tl.decode(spn.tile_lists_of(nb), B, N, K)
-            assert flag == 0 and max_total + 1 > tl.TILE_CAP
+            assert flag == want_flag and max_total + 1 > tl.TILE_CAP
+            assert (max_total + 1 > tl.MAX_SLOTS) == bool(want_flag)
+            low, gd = oracle.grid_bounds(locs, 0.1, 96)
+            ids, oi = oracle.hashgrid_order(locs, low, gd, 0.1, stable=True)
+            nl, _ = oracle.reorder_data(locs, None, oi)
+            onb, _, _ = oracle.compute_collisions(nl, nl, low, gd, ids, 0.1, 0.1, K, 0, 96 ** 3)
+            gu.assert_bit_equal(gu.host(nb), onb, "rows of oversized blocks")
+            have = counts >= 0
+            assert np.array_equal(dec[have], onb.astype(np.int64)[have])
         l = sl.detach().clone().requires_grad_(True)
         ones = torch.ones(B, N, 1, device="cuda")
         outs = group(l, [sv, ones], nb)

@@ -81,8 +81,13 @@ def test_search_pipeline_bit_exact(spn, oracle, B, N, M, D, C, extent, radius, G
                                                          radius, K, include_self, G ** D)
                 # oracle leaves entries after the terminator at their -1 pre-fill: full rows compare
                 gu.assert_bit_equal(gu.host(coll), o_coll, "neighbour rows K=%d self=%d" % (K, include_self))
+                # the flag says "the relation may not be symmetric": a row was cut at K, or a query lies two or
+                # more cells beyond the upper border of a clamped grid (it then sees no cell at all while the
+                # border cell it was hashed into is still scanned by its neighbours)
                 full = bool((o_coll[..., K - 1] >= 0).any())
-                assert bool(flag.item()) == full, "truncation flag"
+                gq = np.trunc((q_np - o_low[:, None, :]) / np.float32(radius))
+                beyond = bool(((o_gd[:, None, :] > 0) & (gq >= o_gd[:, None, :] + 1)).any())
+                assert bool(flag.item()) == (full or beyond), "asymmetry flag"
 
 
 def test_module_api_reference_test_shape(spn, oracle):
@@ -199,11 +204,18 @@ def test_tile_lists_describe_the_same_lists(spn, B, N, D, extent, radius, K, inc
     flag, counts, dec, max_total = tl.decode(tiles, B, N, K)
     nbh = gu.host(nb).astype(np.int64)
     want_cnt = (nbh >= 0).sum(2)
-    assert np.array_equal(counts, want_cnt), "list lengths"
+    have = counts >= 0  # blocks with more than 4096 candidates (clamped border cells) carry no tile rows
+    assert bool(flag & 2) == (not have.all()), "capacity bit of the tile flag"
+    assert np.array_equal(counts[have], want_cnt[have]), "list lengths"
     truncated = bool((nbh[..., K - 1] >= 0).any())
-    assert bool(flag & 1) == truncated, "truncation bit of the tile flag"
-    assert not (flag & 2), "16-bit slots suffice"
-    assert np.array_equal(dec, nbh), "decoded tile lists == float lists"
+    low, gd, slh = gu.host(coll.last_lower_bounds), gu.host(coll.last_grid_dims), gu.host(sl)
+    gq = np.trunc((slh - low[:, None, :]) / np.float32(radius))
+    beyond = bool(((gd[:, None, :] > 0) & (gq >= gd[:, None, :] + 1)).any())
+    assert bool(flag & 1) == (truncated or beyond), "asymmetry bit of the tile flag"
+    assert bool(spn.sym_flag_of(nb).item()) == (truncated or beyond)
+    assert not (flag & ~3), "no inconsistency"
+    assert have.all() or N == 4099, "only the clamped-grid case has blocks beyond the format's capacity"
+    assert np.array_equal(dec[have], nbh[have]), "decoded tile lists == float lists"
     # the plain entry point writes the same float rows
     coll2 = spn.ParticleCollision(D, radius, max_grid_dim=G, max_collisions=K, include_self=bool(include_self)).cuda()
     coll2.tile_lists = False
@@ -221,39 +233,37 @@ def test_tile_lists_full_size(spn):
     sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
     tiles = spn.tile_lists_of(nb)
     assert int(tiles[:4].view(torch.int32).item()) == 0
-    lay = tl.layout(B, N, K)
     raw = tiles.cpu().numpy()
-    desc = raw[lay["desc_off"]:lay["cnt_off"]].view(np.int32).reshape(B, lay["ntb"], tl.DESC_INTS)
+    desc, goff, maxcnt, sumcnt = tl.descriptors(raw, B, N, K)
     totals = desc[:, :, 1]
-    assert totals.min() > 0
-    assert (totals + 1 > tl.TILE_CAP).mean() < 0.01, "tiles that do not fit the staging capacity are rare"
-    counts = raw[lay["cnt_off"]:lay["cnt_off"] + 4 * B * N].view(np.int32).reshape(B, N)
-    assert np.array_equal(counts, gu.host((nb >= 0).sum(2)))
-    # decode the first 24 tile blocks of scene 5 (python loop): assemble a small one-scene buffer
-    b, nt = 5, 24
-    Ns = nt * tl.TILE_Q
-    l1 = tl.layout(1, Ns, K)
-    one = np.zeros(l1["total"], np.uint8)
-    one[l1["desc_off"]:l1["cnt_off"]] = desc[b, :nt].copy().reshape(-1).view(np.uint8)
-    one[l1["cnt_off"]:l1["cnt_off"] + 4 * Ns] = counts[b, :Ns].copy().view(np.uint8)
-    s0 = lay["list_off"] + b * lay["ntb"] * tl.TILE_Q * K * 2
-    one[l1["list_off"]:] = raw[s0:s0 + nt * tl.TILE_Q * K * 2]
-    flag, c1, dec, _ = tl.decode(one, 1, Ns, K)
-    assert np.array_equal(dec[0], gu.host(nb[b, :Ns]).astype(np.int64))
+    assert totals.min() > 0 and totals.max() + 1 <= tl.MAX_SLOTS
+    assert (totals + 1 > tl.TILE_CAP).mean() < 0.005, "blocks that need more than one staged chunk are rare"
+    cnt = gu.host((nb >= 0).sum(2)).reshape(B, -1, tl.TILE_Q)
+    assert np.array_equal(sumcnt, cnt.sum(2)) and np.array_equal(maxcnt, cnt.max(2))
+    # rows actually stored per block vs the entries they hold: the cost of rank-ordered octiles
+    slots = goff[:, :, tl.OCTILES].astype(np.int64).sum() * 32
+    assert slots < 1.25 * sumcnt.sum(), "octile padding stays below 25 %% (%.3f)" % (slots / sumcnt.sum())
+    blocks = [(5, tb) for tb in range(24)] + [(7, lay) for lay in (1000, 1023)]
+    flag, c1, dec, _ = tl.decode(raw, B, N, K, blocks=blocks)
+    nbh = gu.host(nb).astype(np.int64)
+    for b, tb in blocks:
+        sl_ = slice(tb * tl.TILE_Q, (tb + 1) * tl.TILE_Q)
+        assert np.array_equal(dec[b, sl_], nbh[b, sl_])
 
 
-def test_lazy_tile_lists_are_not_built_from_stale_scratch(spn):
-    """Default mode: the sidecar is built on first request from the module's scratch (sorted keys, cell table);
-    once the module has run again that scratch describes another call, so the request must be refused."""
+def test_tile_lists_belong_to_their_call(spn):
+    """The sidecar is written together with the rows and owns its buffer: a later forward() of the same module
+    must not change what an earlier neighbour tensor's sidecar says."""
+    from smoothparticlenets_b200 import tile_lists as tl
     B, N = 2, 500
     a, _, _ = cases.collision_case(21, B=B, N=N, M=1, D=3, C=1)
     b, _, _ = cases.collision_case(22, B=B, N=N, M=1, D=3, C=1)
     coll = spn.ParticleCollision(3, 0.1).cuda()
-    assert coll.tile_lists == "lazy"
+    assert coll.tile_lists is True
     _, _, nb1 = coll(gu.dev(a))
-    from smoothparticlenets_b200 import sidecar
-    assert sidecar.lookup(nb1).tiles is None, "nothing is built until somebody asks"
+    t1 = spn.tile_lists_of(nb1)
+    before = t1.clone()
     _, _, nb2 = coll(gu.dev(b))
-    assert spn.tile_lists_of(nb1) is None
-    t2 = spn.tile_lists_of(nb2)
-    assert t2 is not None and spn.tile_lists_of(nb2) is t2, "built once, cached on the tensor"
+    assert spn.tile_lists_of(nb1) is t1 and torch.equal(t1, before)
+    assert np.array_equal(tl.decode(t1, B, N, 128)[2], gu.host(nb1).astype(np.int64))
+    assert np.array_equal(tl.decode(spn.tile_lists_of(nb2), B, N, 128)[2], gu.host(nb2).astype(np.int64))

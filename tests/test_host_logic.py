@@ -127,14 +127,15 @@ def test_tile_list_layout_mirror_matches_library(spn):
     from smoothparticlenets_b200 import _native as nat, tile_lists as tl
     L = nat.lib()
     for B, N, D, K in [(1, 1, 3, 16), (2, 1000, 3, 128), (8, 65536, 3, 128), (3, 777, 2, 64), (2, 300, 1, 32),
-                       (1, 4099, 3, 256)]:
+                       (1, 4099, 3, 256), (1, 100, 3, 77)]:
         assert L.spnb_tile_lists_bytes(B, N, D, K) == tl.layout(B, N, K)["total"], (B, N, D, K)
     assert L.spnb_tile_lists_bytes(1, 100, 4, 128) == 0    # ndims > 3
-    assert L.spnb_tile_lists_bytes(1, 100, 3, 100) == 0    # max_collisions not a multiple of 16
-    assert L.spnb_tile_lists_bytes(1, 100, 3, 8) == 0
+    assert L.spnb_tile_lists_bytes(1, 100, 3, 1000) == 0   # longer lists than the format is built for
+    assert L.spnb_tile_lists_bytes(1, 100, 3, 100) > 0     # any max_collisions up to 512
     assert L.spnb_tile_lists_bytes(0, 100, 3, 128) == 0
     # null pointers are rejected on the host
-    assert L.spnb_build_tile_lists(None, None, None, None, None, 1, 100, 3, 128, 96 ** 3, None, 0, None) == 0
+    assert L.spnb_compute_collisions_tiled(None, None, None, None, None, None, None, None, 1, 100, 3, 128, 96 ** 3,
+                                           0.1, 0.1, 0, None, None, 0, None) == 0
     assert b"null pointer" in L.spnb_last_error()
     assert L.spnb_pbf_stage1_forward(None, None, None, None, None, None, None, 10, 3, 1.0, 1.0, None) == 0
     assert b"bad arguments" in L.spnb_last_error()
