@@ -74,6 +74,8 @@ def build_library(force=False, verbose=False, extra_flags=()):
     call it at start-up): an exclusive file lock serialises them, and the up-to-date check does not depend
     on where the repository is mounted (the GPU box runs a copy under another path)."""
     import fcntl
+    if os.environ.get("SPNB_NO_BUILD") and os.path.exists(LIB_PATH):
+        return LIB_PATH  # use the prebuilt (variant) library as it is
     os.makedirs(OBJ, exist_ok=True)
     with open(os.path.join(OBJ, "build.lock"), "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)

@@ -642,25 +642,17 @@ __device__ __forceinline__ void tile_stage(const float4* __restrict__ planes, si
 // are slot 0, the sentinel record: they fail every radius test).
 constexpr int kTileStageBytes = 8 * 1024;  // per CTA, whatever G: warps * NO * 2 buffers * 512 bytes
 
-template <int G, typename Body>
-__device__ __forceinline__ void tile_walk(const unsigned char* __restrict__ rows, const TileDesc& d,
-                                          unsigned char* __restrict__ stage_cta, Body body)
-{
-    constexpr int NO = 4 / G, LPO = 32 / NO;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int o = lane / LPO, li = lane % LPO;
-    unsigned char* stage = stage_cta + warp * (NO * 1024);
+template <int G>
+struct TileWalk {
+    static constexpr int NO = 4 / G, LPO = 32 / NO;
     int S[NO], R0[NO];
-    int smax_all = 0, my_s = 0;
-#pragma unroll
-    for (int oo = 0; oo < NO; ++oo) {
-        R0[oo] = d.goff[warp * NO + oo];
-        S[oo] = d.goff[warp * NO + oo + 1] - R0[oo];
-        smax_all = max(smax_all, S[oo]);
-        if (oo == o) my_s = S[oo];
-    }
-    const int nch = (smax_all + 7) >> 3;
-    auto issue = [&](int c) {
+    int smax_all, my_s, nch;
+    unsigned char* stage;
+    const unsigned char* rows;
+
+    __device__ __forceinline__ void issue(int c) const
+    {
+        const int lane = threadIdx.x & 31;
 #pragma unroll
         for (int oo = 0; oo < NO; ++oo) {
             const int nrows = min(8, S[oo] - 8 * c);
@@ -669,44 +661,74 @@ __device__ __forceinline__ void tile_walk(const unsigned char* __restrict__ rows
                            rows + (size_t)(R0[oo] + 8 * c) * kTileRowBytes + lane * 16);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if (nch > 0) issue(0);
-    for (int c = 0; c < nch; ++c) {
-        __syncwarp();  // every lane is done with the buffer the next copy overwrites
-        if (c + 1 < nch) {
-            issue(c + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    // reads the octile row counts and requests the first 8 rows of every octile of this warp
+    __device__ __forceinline__ void begin(const unsigned char* __restrict__ rows_, const TileDesc& d,
+                                          unsigned char* __restrict__ stage_cta)
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int o = lane / LPO;
+        rows = rows_;
+        stage = stage_cta + warp * (NO * 1024);
+        smax_all = 0;
+        my_s = 0;
+#pragma unroll
+        for (int oo = 0; oo < NO; ++oo) {
+            R0[oo] = d.goff[warp * NO + oo];
+            S[oo] = d.goff[warp * NO + oo + 1] - R0[oo];
+            smax_all = max(smax_all, S[oo]);
+            if (oo == o) my_s = S[oo];
         }
-        __syncwarp();
-        const unsigned char* buf = stage + (o * 2 + (c & 1)) * 512 + li * (8 / G);
-        const int ns = min(8, my_s - 8 * c);  // steps of MY octile in this chunk (<= 0: none)
-        if (G == 4) {
-            // one entry per lane and step: two steps per iteration, the second gather issued before the first
-            // pair's arithmetic
-#pragma unroll 1
-            for (int s_ = 0; s_ < ns; s_ += 2) {
-                const unsigned e0 = *reinterpret_cast<const unsigned short*>(buf + s_ * kTileRowBytes);
-                const unsigned e1 = s_ + 1 < ns ? *reinterpret_cast<const unsigned short*>(buf + (s_ + 1) * kTileRowBytes) : 0u;
-                body(e0, e1);
+        nch = (smax_all + 7) >> 3;
+        if (nch > 0) issue(0);
+    }
+    // `first`: chunk 0 is already in flight (begin() requested it)
+    template <typename Body>
+    __device__ __forceinline__ void run(bool first, Body body) const
+    {
+        const int lane = threadIdx.x & 31;
+        const int o = lane / LPO, li = lane % LPO;
+        if (!first && nch > 0) {
+            __syncwarp();
+            issue(0);
+        }
+        for (int c = 0; c < nch; ++c) {
+            __syncwarp();  // every lane is done with the buffer the next copy overwrites
+            if (c + 1 < nch) {
+                issue(c + 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
-        } else if (G == 2) {
+            __syncwarp();
+            const unsigned char* buf = stage + (o * 2 + (c & 1)) * 512 + li * (8 / G);
+            const int ns = min(8, my_s - 8 * c);  // steps of MY octile in this chunk (<= 0: none)
+            if (G == 4) {
+                // one entry per lane and step: two steps per iteration, so that the second gather is issued
+                // before the first pair's arithmetic
 #pragma unroll 1
-            for (int s_ = 0; s_ < ns; ++s_) {
-                const unsigned w = *reinterpret_cast<const unsigned*>(buf + s_ * kTileRowBytes);
-                body(w & 0xffffu, w >> 16);
-            }
-        } else {
+                for (int s_ = 0; s_ < ns; s_ += 2) {
+                    const unsigned e0 = *reinterpret_cast<const unsigned short*>(buf + s_ * kTileRowBytes);
+                    const unsigned e1 = s_ + 1 < ns ? *reinterpret_cast<const unsigned short*>(buf + (s_ + 1) * kTileRowBytes) : 0u;
+                    body(e0, e1);
+                }
+            } else if (G == 2) {
 #pragma unroll 1
-            for (int s_ = 0; s_ < ns; ++s_) {
-                const uint2 w = *reinterpret_cast<const uint2*>(buf + s_ * kTileRowBytes);
-                body(w.x & 0xffffu, w.x >> 16);
-                body(w.y & 0xffffu, w.y >> 16);
+                for (int s_ = 0; s_ < ns; ++s_) {
+                    const unsigned w = *reinterpret_cast<const unsigned*>(buf + s_ * kTileRowBytes);
+                    body(w & 0xffffu, w >> 16);
+                }
+            } else {
+#pragma unroll 1
+                for (int s_ = 0; s_ < ns; ++s_) {
+                    const uint2 w = *reinterpret_cast<const uint2*>(buf + s_ * kTileRowBytes);
+                    body(w.x & 0xffffu, w.x >> 16);
+                    body(w.y & 0xffffu, w.y >> 16);
+                }
             }
         }
     }
-}
+};
 
 // Query of this thread: rank order within the block (tile_lists.cuh).  Returns the query's index within the block.
 template <int G>
@@ -715,14 +737,14 @@ __device__ __forceinline__ int tile_my_query(const unsigned char* __restrict__ b
     constexpr int NO = 4 / G, LPO = 32 / NO;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rank = 8 * (warp * NO + lane / LPO) + (lane % LPO) / G;
-    return (int)blob[rank];
+    return (int)__ldg(blob + rank);
 }
 
 // The common frame of the two tile kernels: descriptor, records staged chunk by chunk, the walk.  `pair2(ra, rb)`
 // consumes two gathered records.
 template <int V, int G, typename Pair>
 __device__ __forceinline__ void tile_run(const float4* __restrict__ planes, long long BN, size_t scene_off,
-                                         const TileDesc& s_desc, const unsigned char* blob, unsigned char* s_raw,
+                                         const TileDesc& s_desc, const TileWalk<G>& W, unsigned char* s_raw,
                                          unsigned long long* s_bar, Pair& P)
 {
     const int tid = threadIdx.x;
@@ -742,7 +764,7 @@ __device__ __forceinline__ void tile_run(const float4* __restrict__ planes, long
             const unsigned t = e - cb;
             return t < (kTileCap - 1) * 16u ? t + 16u : 0u;
         };
-        tile_walk<G>(blob + kTileHeaderBytes, s_desc, s_raw + V * (kTileCap * 16), [&](unsigned ea, unsigned eb) {
+        W.run(chunk == 0, [&](unsigned ea, unsigned eb) {
             const unsigned sa = nchunks > 1 ? local(ea) : ea, sb = nchunks > 1 ? local(eb) : eb;
             float ra[V * 4], rb[V * 4];
 #pragma unroll
@@ -774,9 +796,12 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     const int tid = threadIdx.x, tb = blockIdx.x, b = blockIdx.y;
     // the descriptor load is issued together with the flag load (both are inputs of this call's
     // predecessors only), so the flag test does not add a global-memory latency to the prologue
-    int desc_word = 0;
-    if (ta.flag != nullptr && tid < 32)
-        desc_word = __ldg(reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb) + tid);
+    int desc_word = 0, ql = 0;
+    const unsigned char* blob = ta.blobs + ((size_t)b * ta.ntb + tb) * ta.blob_stride;
+    if (ta.flag != nullptr) {
+        if (tid < 32) desc_word = __ldg(reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb) + tid);
+        ql = tile_my_query<G>(blob);  // my query (rank order); issued with the descriptor load
+    }
     if (!tiles_usable(ta.flag, nullptr, false)) {
         // no usable tile lists for this call (a list reached K, ...): the float-list walk, strided over the
         // grid, with the (unused) tile buffer as its row-staging scratch; records are record-major then
@@ -795,9 +820,10 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     __syncthreads();
     const float4* planes = reinterpret_cast<const float4*>(rec);
     if (tid < 32) tile_stage<V>(planes, (size_t)BN, (size_t)b * N, s_desc, 0, s_rec, &s_bar);
+    TileWalk<G> W;
+    W.begin(blob + kTileHeaderBytes, s_desc, s_raw + V * (kTileCap * 16));  // first list rows in flight
 
-    const unsigned char* blob = ta.blobs + ((size_t)b * ta.ntb + tb) * ta.blob_stride;
-    const int ql = tile_my_query<G>(blob), sub = tid % G;
+    const int sub = tid % G;
     const int m = tb * kTileQ + ql;
     const bool active = m < N;
     const size_t q = (size_t)b * N + (active ? m : 0);
@@ -809,7 +835,7 @@ k_tile_fwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
 #pragma unroll
         for (int k = 0; k < D; ++k) P.x[k] = t[k];
     }
-    tile_run<V, G>(planes, BN, (size_t)b * N, s_desc, blob, s_raw, &s_bar, P);
+    tile_run<V, G>(planes, BN, (size_t)b * N, s_desc, W, s_raw, &s_bar, P);
     P.template finish<G>(ga, q, active, sub);
 }
 
@@ -824,9 +850,12 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     __shared__ TileDesc s_desc;
     __shared__ __align__(8) unsigned long long s_bar;
     const int tid = threadIdx.x, tb = blockIdx.x, b = blockIdx.y;
-    int desc_word = 0;
-    if (ta.flag != nullptr && tid < 32)
-        desc_word = __ldg(reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb) + tid);
+    int desc_word = 0, ql = 0;
+    const unsigned char* blob = ta.blobs + ((size_t)b * ta.ntb + tb) * ta.blob_stride;
+    if (ta.flag != nullptr) {
+        if (tid < 32) desc_word = __ldg(reinterpret_cast<const int*>(ta.descs + (size_t)b * ta.ntb + tb) + tid);
+        ql = tile_my_query<G>(blob);  // my query (rank order); issued with the descriptor load
+    }
     if (!tiles_usable(ta.flag, sym_flag, true)) {
         // no usable tile lists for this call, or the relation is not symmetric (the tile path only has the
         // gather mode): the float-list walk (gather or atomics mode by sym_flag)
@@ -845,9 +874,10 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
     __syncthreads();
     const float4* planes = reinterpret_cast<const float4*>(rec);
     if (tid < 32) tile_stage<V>(planes, (size_t)BN, (size_t)b * N, s_desc, 0, s_rec, &s_bar);
+    TileWalk<G> W;
+    W.begin(blob + kTileHeaderBytes, s_desc, s_raw + V * (kTileCap * 16));  // first list rows in flight
 
-    const unsigned char* blob = ta.blobs + ((size_t)b * ta.ntb + tb) * ta.blob_stride;
-    const int ql = tile_my_query<G>(blob), sub = tid % G;
+    const int sub = tid % G;
     const int m = tb * kTileQ + ql;
     const bool active = m < N;
     const size_t q = (size_t)b * N + (active ? m : 0);
@@ -858,7 +888,7 @@ k_tile_bwd(const float* __restrict__ rec, TileArgs ta, GroupArgs ga, int N, int 
         const float4 t = planes[(size_t)v * BN + q];
         P.me[4 * v] = t.x; P.me[4 * v + 1] = t.y; P.me[4 * v + 2] = t.z; P.me[4 * v + 3] = t.w;
     }
-    tile_run<V, G>(planes, BN, (size_t)b * N, s_desc, blob, s_raw, &s_bar, P);
+    tile_run<V, G>(planes, BN, (size_t)b * N, s_desc, W, s_raw, &s_bar, P);
     P.template finish<G>(ga, dlocs, q, active, sub);
 }
 

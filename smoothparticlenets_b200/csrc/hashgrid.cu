@@ -792,10 +792,12 @@ k_collide_tiles(const float4* __restrict__ pos4, const float* __restrict__ locs,
 {
     constexpr int D = DT;
     extern __shared__ __align__(128) unsigned char s_raw[];
+    // A candidate / hit is a 16-bit code: tile slot (12 bits) | range of the block it lies in (4 bits); the range
+    // gives the sorted particle index back with one addition (s_shift), the slot is what the tile rows store.
     float4* s_pos = reinterpret_cast<float4*>(s_raw);                                  // [kTileCap]
-    int* s_slot2idx = reinterpret_cast<int*>(s_raw + kTileCap * 16);                   // [kTileCap]
-    unsigned short* s_cand = reinterpret_cast<unsigned short*>(s_raw + kTileCap * 20); // [8][kCtWin]
+    unsigned short* s_cand = reinterpret_cast<unsigned short*>(s_raw + kTileCap * 16); // [8][kCtWin]
     unsigned short* s_hits = s_cand + 8 * kCtWin;                                      // [kTileQ][K]
+    __shared__ int s_shift[kTileMaxRanges];  // sorted index = slot + s_shift[range]
     __shared__ TileDesc s_desc;
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ int s_cnt[kTileQ];
@@ -860,18 +862,8 @@ k_collide_tiles(const float4* __restrict__ pos4, const float* __restrict__ locs,
         }
     }
     if (tid == 0) s_pos[0] = make_float4(1e18f, 1e18f, 1e18f, 0.0f);
-    for (int r = 0; r < s_desc.nr && staged; ++r) {
-        const int len = s_desc.prefix[r + 1] - s_desc.prefix[r];
-        for (int i = tid; i < len; i += kCtThreads) s_slot2idx[1 + s_desc.prefix[r] + i] = s_desc.start[r] + i;
-    }
-    // sorted particle index of slot >= 1 (blocks that are not staged have no table)
-    auto slot_index = [&](unsigned slot) {
-        const int p = (int)slot - 1;
-        int idx = 0;
-        for (int r = 0; r < s_desc.nr; ++r)
-            if (p >= s_desc.prefix[r]) idx = s_desc.start[r] + p - s_desc.prefix[r];
-        return idx;
-    };
+    if (tid < kTileMaxRanges) s_shift[tid] = s_desc.start[tid] - s_desc.prefix[tid] - 1;
+    auto code_index = [&](unsigned code) { return (int)(code & 0xfffu) + s_shift[code >> 12]; };
     // ---- my warp's 8 queries: lanes 0..7 hold one each
     const int w0 = warp * 8;
     const int nqw = max(0, min(8, nq - w0));
@@ -933,7 +925,7 @@ k_collide_tiles(const float4* __restrict__ pos4, const float* __restrict__ locs,
                         bad = true;  // never expected: the cell is not inside the block's ranges
                         cnt = 0;
                     }
-                    slot0 = cstart - s0 + p0 + 1;
+                    slot0 = (cstart - s0 + p0 + 1) | (g << 12);
                 }
             }
         }
@@ -961,10 +953,10 @@ k_collide_tiles(const float4* __restrict__ pos4, const float* __restrict__ locs,
 #pragma unroll
             for (int i = 0; i < kCtWin / 32; ++i) {
                 const int t = i * 32 + lane;
-                cs[i] = t < wn ? cand[t] : 0u;
+                cs[i] = t < wn ? cand[t] : 0u;  // code 0: the sentinel, far outside every radius
                 float4 p;
-                if (staged) p = s_pos[cs[i]];
-                else p = cs[i] ? pos4[sb + slot_index(cs[i])] : make_float4(1e18f, 1e18f, 1e18f, 0.0f);
+                if (staged) p = s_pos[cs[i] & 0xfffu];
+                else p = cs[i] ? pos4[sb + code_index(cs[i])] : make_float4(1e18f, 1e18f, 1e18f, 0.0f);
                 const float tt[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
                 for (int k = 0; k < D; ++k) px[i][k] = tt[k];
@@ -976,21 +968,28 @@ k_collide_tiles(const float4* __restrict__ pos4, const float* __restrict__ locs,
 #pragma unroll
                 for (int k = 0; k < D; ++k) x[k] = __shfl_sync(0xffffffffu, myx[k], qi + r);
                 unsigned short* hrow = s_hits + (size_t)(w0 + qi + r) * K;
+                // all distance tests first (no dependence between chunks), then the ordered compaction
+                unsigned m[kCtWin / 32], mine = 0;
 #pragma unroll
                 for (int i = 0; i < kCtWin / 32; ++i) {
-                    if (i * 32 < wn && found < K) {
+                    m[i] = 0;
+                    if (i * 32 < wn) {
                         float d = 0.0f;
 #pragma unroll
                         for (int k = 0; k < D; ++k) {
                             const float nr = x[k] - px[i][k];
                             d += nr * nr;
                         }
-                        const bool hit = (i * 32 + lane < wn) && d < r2 && (d > 0.0f || include_self);
-                        const unsigned m = __ballot_sync(0xffffffffu, hit);
-                        const int pos = found + __popc(m & lanemask_lt());
-                        if (hit && pos < K) hrow[pos] = (unsigned short)cs[i];
-                        found += __popc(m);
+                        const bool hit = d < r2 && (d > 0.0f || include_self);
+                        m[i] = __ballot_sync(0xffffffffu, hit);
+                        mine |= (hit ? 1u : 0u) << i;
                     }
+                }
+#pragma unroll
+                for (int i = 0; i < kCtWin / 32; ++i) {
+                    const int pos = found + __popc(m[i] & lanemask_lt());
+                    if (((mine >> i) & 1u) && pos < K) hrow[pos] = (unsigned short)cs[i];
+                    found += __popc(m[i]);
                 }
                 if (lane == qi + r) myfound = found;
             }
@@ -1041,16 +1040,26 @@ k_collide_tiles(const float4* __restrict__ pos4, const float* __restrict__ locs,
     __syncthreads();
 
     // ---- float rows: accepted particle indices in the reference's order, then -1 up to the end of the row
+    const bool vec_rows = (K & 3) == 0 && (reinterpret_cast<size_t>(coll) & 15) == 0;
     for (int r = 0; r < 8; ++r) {
         const int ql = w0 + r;
         if (ql >= nq) break;
         const int c = s_cnt[ql];
         float* row = coll + (sb + q0 + ql) * K;
         const unsigned short* hrow = s_hits + (size_t)ql * K;
-        if (staged) {
-            for (int k = lane; k < K; k += 32) row[k] = k < c ? (float)s_slot2idx[hrow[k]] : -1.0f;
+        if (vec_rows) {
+            for (int k4 = lane; k4 * 4 < K; k4 += 32) {
+                const uint2 h = *reinterpret_cast<const uint2*>(hrow + 4 * k4);
+                const int k = 4 * k4;
+                float4 v;
+                v.x = k + 0 < c ? (float)code_index(h.x & 0xffffu) : -1.0f;
+                v.y = k + 1 < c ? (float)code_index(h.x >> 16) : -1.0f;
+                v.z = k + 2 < c ? (float)code_index(h.y & 0xffffu) : -1.0f;
+                v.w = k + 3 < c ? (float)code_index(h.y >> 16) : -1.0f;
+                *reinterpret_cast<float4*>(row + k) = v;
+            }
         } else {
-            for (int k = lane; k < K; k += 32) row[k] = k < c ? (float)slot_index(hrow[k]) : -1.0f;
+            for (int k = lane; k < K; k += 32) row[k] = k < c ? (float)code_index(hrow[k]) : -1.0f;
         }
     }
     // ---- tile rows of octile `warp`: entry 4s+e of rank 8g+r at position 4r+e of row goff[g]+s
@@ -1063,7 +1072,7 @@ k_collide_tiles(const float4* __restrict__ pos4, const float* __restrict__ locs,
         unsigned short* rows = reinterpret_cast<unsigned short*>(blob + kTileHeaderBytes) + (size_t)s_desc.goff[g] * 32;
         for (int s_ = 0; s_ < S; ++s_) {
             const int e = 4 * s_ + (lane & 3);
-            rows[s_ * 32 + lane] = e < c ? (unsigned short)(hrow[e] << 4) : (unsigned short)0;
+            rows[s_ * 32 + lane] = e < c ? (unsigned short)((hrow[e] & 0xfffu) << 4) : (unsigned short)0;
         }
     }
     if (tid < kTileQ) blob[tid] = s_perm[tid];
@@ -1318,7 +1327,7 @@ int spnb_compute_collisions_tiled(const float* pos4, const float* locs, const fl
     k_table_fill<<<dim3(cdiv(N, 256), B), 256, 0, stream>>>((const uint32_t*)cellIDs, grid_dims, cellStarts,
                                                             cellEnds, N, D, ncells);
     const float r2 = radius * radius;
-    size_t smem = (size_t)kTileCap * 20 + 8 * kCtWin * 2 + (size_t)kTileQ * K * 2;
+    size_t smem = (size_t)kTileCap * 16 + 8 * kCtWin * 2 + (size_t)kTileQ * K * 2;
     const dim3 grid(tl.ntb, B);
 #define SPNB_CT(DT)                                                                                              \
     do {                                                                                                         \

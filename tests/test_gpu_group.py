@@ -132,12 +132,13 @@ def test_group_tile_flag_falls_back_on_device(spn):
         if tiles_on:
             assert int(spn.tile_lists_of(nb)[:4].view(torch.int32).item()) != 0
         l = sl.detach().clone().requires_grad_(True)
-        ones = torch.ones(B, N, 1, device="cuda")
-        outs = group(l, [sv, ones], nb)
+        n0 = nat.lib().spnb_launch_count()
+        outs = group(l, [sv, None], nb)
+        assert nat.lib().spnb_launch_count() - n0 == 2, "fused path"
         torch.autograd.backward(outs, [torch.ones_like(o) for o in outs])
         res[tiles_on] = ([o.detach() for o in outs], l.grad.clone())
     for a, b in zip(res[True][0], res[False][0]):
-        assert torch.equal(a, b)
+        assert torch.equal(a, b), "the same float-list walk with and without (unusable) tile lists"
     # lists are cut at K here, so the backward is the atomics mode in both runs: order-dependent rounding
     close(res[True][1], res[False][1], "locs.grad", k=64)
 
@@ -173,8 +174,7 @@ def test_group_oversized_tiles(spn, oracle, N, K, want_flag):
             have = counts >= 0
             assert np.array_equal(dec[have], onb.astype(np.int64)[have])
         l = sl.detach().clone().requires_grad_(True)
-        ones = torch.ones(B, N, 1, device="cuda")
-        outs = group(l, [sv, ones], nb)
+        outs = group(l, [sv, None], nb)
         torch.autograd.backward(outs, [torch.ones_like(o) for o in outs])
         res[tiles_on] = ([o.detach() for o in outs], l.grad.clone())
     for i, (a, b) in enumerate(zip(res[True][0], res[False][0])):

@@ -83,29 +83,46 @@ def test_c2_full_scene_vs_oracle(spn, oracle):
         close(lt.grad, want[(kernel, C, normed)][1], "dlocs %s C=%d" % (kernel, C), k=4)
         close(dt.grad, dd, "ddata %s C=%d" % (kernel, C), k=4)
 
-    # ---- the fused groups of the fluid step on the same scene (tile lists, TMA-staged tiles)
+    # ---- the fused groups of the fluid step on the same scene (tile lists, TMA-staged tiles), with the data
+    # pattern fluidstep.FluidStep feeds them: None = ones, the position tensor itself, or a data tensor
+    from smoothparticlenets_b200 import _native as nat
     tiles = spn.tile_lists_of(nb)
     assert tiles is not None and int(tiles[:4].view(torch.int32).item()) == 0, "tile lists usable at c2"
+    press = r.rand(B, N, 1).astype(np.float32)
+    xp = (nl * press).astype(np.float32)
+    LOCS = "locs"
     groups = [
-        [("spiky", 1, False), ("dspiky", D, True), ("dspiky", 1, True), ("cohesion", D, True),
-         ("cohesion", 1, True), ("constant", 1, False)],
-        [("dspiky", D, True), ("dspiky", 1, True)], [("constant", D, False)], [("spiky", D, False), ("spiky", 1, False)]]
-    for specs in groups:
-        group = spn.ConvSPGroup([layers[s] for s in specs])
+        [(("spiky", 1, False), None), (("dspiky", D, True), LOCS), (("dspiky", 1, True), None),
+         (("cohesion", D, True), LOCS), (("cohesion", 1, True), None), (("constant", 1, False), None)],
+        [(("dspiky", D, True), xp), (("dspiky", 1, True), press)],
+        [(("constant", D, False), nv)],
+        [(("spiky", D, False), nv), (("spiky", 1, False), None)]]
+    for gi, specs in enumerate(groups):
+        group = spn.ConvSPGroup([layers[s] for s, _ in specs])
         lt = sl.detach().clone().requires_grad_(True)
-        # D-channel layers: a data tensor; one-channel layers: None = ones (what fluidstep.FluidStep passes)
-        datas = [gu.dev(want[s][4]).requires_grad_(True) if s[1] == D else None for s in specs]
-        from smoothparticlenets_b200 import _native as nat
+        datas, refs = [], []
+        for (kernel, C, normed), d in specs:
+            dn = scal if d is None else (nl if d is LOCS else d)
+            datas.append(None if d is None else (lt if d is LOCS else gu.dev(d).requires_grad_(True)))
+            w = np.eye(C, dtype=np.float32).reshape(C, C, 1)
+            go = cases.rng(50 + 7 * gi + C).rand(B, N, C).astype(np.float32)
+            fw = oracle.convsp_forward(nl, nl, dn, onb, w, np.zeros(C, np.float32), R, one3, one3, int(normed), kernel)
+            dq, dl, dd, _, _ = oracle.convsp_backward(nl, nl, dn, onb, w, np.zeros(C, np.float32), R, one3, one3,
+                                                      int(normed), kernel, go)
+            refs.append((fw, dq.astype(np.float64) + dl, dd, go))
         n0 = nat.lib().spnb_launch_count()
         outs = group(lt, datas, nb)
         assert nat.lib().spnb_launch_count() - n0 == 2, "pack + one tile kernel"
-        for s, o in zip(specs, outs):
-            close(o, want[s][0], "group fwd %s C=%d" % (s[0], s[1]))
-        torch.autograd.backward(outs, [gu.dev(want[s][3]) for s in specs])
-        close(lt.grad, sum(want[s][1] for s in specs), "group dlocs %s" % (specs,), k=4 * len(specs))
-        for s, d in zip(specs, datas):
-            if d is not None:
-                close(d.grad, want[s][2], "group ddata %s C=%d" % (s[0], s[1]), k=4)
+        for (sp_, d), o, ref in zip(specs, outs, refs):
+            close(o, ref[0], "group %d fwd %s C=%d" % (gi, sp_[0], sp_[1]))
+        torch.autograd.backward(outs, [gu.dev(ref[3]) for ref in refs])
+        # locs.grad: the geometry of every layer + the data gradient of the layers whose data IS the positions
+        want_l = sum(ref[1] for ref in refs) + sum(ref[2].astype(np.float64) for (sp_, d), ref in zip(specs, refs)
+                                                    if d is LOCS)
+        close(lt.grad, want_l, "group %d dlocs" % gi, k=4 * len(specs))
+        for (sp_, d), t, ref in zip(specs, datas, refs):
+            if t is not None and d is not LOCS:
+                close(t.grad, ref[2], "group %d ddata %s C=%d" % (gi, sp_[0], sp_[1]), k=4)
 
 
 # ---------------------------------------------------------------------------------------------------------
