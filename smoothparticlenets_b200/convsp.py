@@ -55,8 +55,12 @@ class ConvSP(torch.nn.Module):
         # Kept for attribute compatibility (convsp.py:85-86); unused.
         self.nshared_device_mem = -1
         self.device_id = -1
-        # extension: False forces the float-list kernels even where the tile kernels apply
-        self.fast_path = True
+        # extension: True routes a kernel_size-1 layer with up to 4 input channels through the single-layer
+        # signature of the tile kernels (pack pre-pass + k_tile_fwd / k_tile_bwd) when the neighbour tensor carries
+        # tile lists.  Measured on B200 (profiles/README.md) a single layer gains nothing from it -- the pack
+        # pre-pass costs what the tile kernel saves -- so it is off by default; ConvSPGroup is where layers
+        # sharing (locs, neighbors) win.
+        self.fast_path = False
 
     def forward(self, locs, data, neighbors, qlocs=None):
         """locs BxNxD, data BxNxC, neighbors BxMxK (float indices, -1 terminated), qlocs BxMxD or

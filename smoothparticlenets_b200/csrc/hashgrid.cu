@@ -655,6 +655,9 @@ k_collide(const float* __restrict__ qlocs, const float* __restrict__ locs,
 // A block whose ranges do not fit the staged tile reads its candidates from global memory; only a block with more
 // than kTileMaxSlots candidates (a dense clump) computes its rows with collide_rows_warp and raises the tile flag.
 constexpr int kCtThreads = 256;
+#ifndef SPNB_CT_MINB
+#define SPNB_CT_MINB 3  // CTAs per SM the register allocation aims at (80 registers)
+#endif
 constexpr int kCtWin = 256;  // candidates held in registers per window (8 per lane)
 
 __device__ __forceinline__ int key_lower_bound(const uint32_t* __restrict__ k, int N, long long v)
@@ -783,7 +786,7 @@ __device__ __forceinline__ void tile_desc_warp(const uint32_t* __restrict__ k, c
 }
 
 template <int DT>
-__global__ void __launch_bounds__(kCtThreads)
+__global__ void __launch_bounds__(kCtThreads, SPNB_CT_MINB)
 k_collide_tiles(const float4* __restrict__ pos4, const float* __restrict__ locs, const float* __restrict__ low,
                 const float* __restrict__ grid_dims, const uint32_t* __restrict__ keys,
                 const float* __restrict__ starts, const float* __restrict__ ends, float* __restrict__ coll, int N,

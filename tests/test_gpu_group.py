@@ -23,7 +23,7 @@ def make_layers(spn, D, specs, r):
 
 
 def close(a, b, what, k=4):
-    b = gu.host(b)
+    b = gu.host(b) if isinstance(b, torch.Tensor) else np.asarray(b)
     gu.assert_close(gu.host(a), b, 1e-5, 1e-6 * k * max(1.0, float(np.abs(b).max())), what)
 
 
@@ -61,8 +61,6 @@ def test_group_matches_per_layer(spn, D, mode):
             l = sl.detach().clone().requires_grad_(True)
             datas = mk(l)
             n0 = nat.lib().spnb_launch_count()
-            for lay in layers:
-                lay.fast_path = False  # the reference side: the per-layer float-list kernels
             outs = group(l, datas, nb) if which == "fused" else tuple(
                 lay(l, ones if d is None else d, nb) for lay, d in zip(layers, datas))
             if which == "fused":  # pack + one walk, not one launch per layer
@@ -286,3 +284,36 @@ def test_fanout_adds_all_gradients(spn, n, shape):
     for w in ws[1:]:
         want = want + w
     close(x.grad, want, "fanout gradient")
+
+
+def test_single_layer_fast_path_option(spn, oracle):
+    """ConvSP.fast_path = True: a kernel_size-1 layer on lists with tile lists runs as pack + tile kernel (the
+    single-layer signature, kernel id at run time) and matches the oracle like the default float-list kernels."""
+    B, N, D, R = 2, 1500, 3, 0.1
+    locs, vel, _ = cases.fluid_cloud(31, B, N)
+    coll = spn.ParticleCollision(D, R, include_self=False).cuda()
+    sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
+    nl, nv, nbh = gu.host(sl), gu.host(sv), gu.host(nb)
+    one3 = np.ones(3, np.float32)
+    for kernel, normed, C, O in (("default", False, 3, 5), ("indirect", True, 3, 2), ("ddefault2", False, 2, 2)):
+        conv = spn.ConvSP(C, O, D, 1, 1, R, dis_norm=normed, kernel_fn=kernel, with_params=False).cuda()
+        r = cases.rng(1)
+        w = r.rand(O, C, 1).astype(np.float32)
+        b = r.rand(O).astype(np.float32)
+        conv.weight.copy_(gu.dev(w))
+        conv.bias.copy_(gu.dev(b))
+        data = nv[..., :C].copy()
+        go = r.rand(B, N, O).astype(np.float32)
+        want = oracle.convsp_forward(nl, nl, data, nbh, w, b, R, one3, one3, int(normed), kernel)
+        dq, dl, dd, _, _ = oracle.convsp_backward(nl, nl, data, nbh, w, b, R, one3, one3, int(normed), kernel, go)
+        for fast in (True, False):
+            conv.fast_path = fast
+            lt = sl.detach().clone().requires_grad_(True)
+            dt = gu.dev(data).requires_grad_(True)
+            n0 = nat.lib().spnb_launch_count()
+            out = conv(lt, dt, nb)
+            assert nat.lib().spnb_launch_count() - n0 == (2 if fast else 1)
+            close(out, want, "%s fast=%s fwd" % (kernel, fast))
+            out.backward(gu.dev(go))
+            close(lt.grad, dq.astype(np.float64) + dl, "%s fast=%s dlocs" % (kernel, fast), k=4)
+            close(dt.grad, dd, "%s fast=%s ddata" % (kernel, fast), k=4)
