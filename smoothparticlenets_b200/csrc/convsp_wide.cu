@@ -22,9 +22,19 @@
 // The contraction is the part that belongs on the tensor cores (tcgen05, 3xTF32 to hold 1e-5); that
 // swap is the next step for this kernel -- the gather phase and the weight streaming are written so
 // that it can be replaced in place (G tile and Wt rows are already K-contiguous in shared/global).
+#include <stdlib.h>
+
 #include "spnb_common.cuh"
 
 namespace spnb {
+
+// convsp_wide_mma.cu: the tcgen05 version (C in {32, 64}, O <= 128)
+bool convsp_wide_mma_supported(int O, int C, int D);
+size_t convsp_wide_mma_workspace_bytes(int O, int C, int ncells);
+int launch_convsp_wide_mma(const float* qlocs, const float* locs, const float* data, const float* neighbors,
+                           const float* weight, const float* bias, int B, int M, int N, int C, int D, int K, int O,
+                           int ncells, float radius, const float* kernel_size, const float* dilation, int dis_norm,
+                           int kernel_fn, float* out, void* workspace, cudaStream_t stream);
 
 namespace {
 
@@ -218,6 +228,8 @@ size_t spnb_convsp_forward_wide_workspace_bytes(int nkernels, int nchannels, int
     // a G tile of at least one cell per slab
     if (ndims < 1 || ndims > 3 || nchannels < 32 || nkernels < 1 || nkernels > 256 || ncells < 1) return 0;
     if ((size_t)kTQ * nchannels * sizeof(float) > (size_t)kMaxGBytes || (nchannels & 3)) return 0;
+    if (convsp_wide_mma_supported(nkernels, nchannels, ndims) && !getenv("SPNB_WIDE_NO_MMA"))
+        return convsp_wide_mma_workspace_bytes(nkernels, nchannels, ncells);
     return sizeof(float) * (size_t)nkernels * nchannels * ncells;
 }
 
@@ -238,6 +250,14 @@ int spnb_convsp_forward_wide(const float* qlocs, const float* locs, const float*
         kernel_fn < 0 || kernel_fn >= SPNB_NUM_KERNEL_FNS) {
         set_error("spnb_convsp_forward_wide: bad arguments (workspace %zu of %zu bytes)", workspace_bytes, need);
         return 0;
+    }
+    if (convsp_wide_mma_supported(O, C, D) && !getenv("SPNB_WIDE_NO_MMA")) {
+        // tensor-core contraction (tcgen05, 3xTF32, accumulators in tensor memory): convsp_wide_mma.cu
+        const int nl = launch_convsp_wide_mma(qlocs, locs, data, neighbors, weight, bias, B, M, N, C, D, K, O, ncells,
+                                              radius, kernel_size, dilation, dis_norm, kernel_fn, out, workspace, stream);
+        if (nl < 0) return 0;
+        count_launches(nl);
+        return check_launch("spnb_convsp_forward_wide") ? 1 : 0;
     }
     const SphParams sp = make_sph_params(kernel_fn, radius);
     float* wt = (float*)workspace;
