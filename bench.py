@@ -496,7 +496,17 @@ def main():
                          "per-layer comparison, no kernel timing, no CPU baseline")
     ap.add_argument("--layerwise", action="store_true",
                     help="headline through the per-layer drop-in modules instead of ConvSPGroup")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2 (default, BASELINE.json configs[1], the headline); c3: ConvSP 64->64 kernel_size 5 "
+                         "(tcgen05 contraction); c5: one scene of 2^24 particles as spatial slabs over --gpus ranks")
+    ap.add_argument("--check", action="store_true",
+                    help="c5 only: run the slab decomposition against the single-GPU computation of the same scene "
+                         "and print parity_ok instead of timing")
+    ap.add_argument("--queries", type=int, default=1 << 17, help="c3: queries evaluated per step")
     args = ap.parse_args()
+    if args.workload != "c2" and args.impl == "ours":
+        import bench_workloads
+        return (bench_workloads.run_c3 if args.workload == "c3" else bench_workloads.run_c5)(args, ClockSampler)
     if args.impl == "reference":
         # bounded sample: each step is one 8192-particle scene per host core (~2.5 s)
         if args.cpu_particles == CPU_SAMPLE_PARTICLES:

@@ -126,10 +126,15 @@ class ParticleCollision(torch.nn.Module):
         self.max_collisions, self.include_self = max_collisions, 1 if include_self else 0
         self.reorder = ReorderData(reverse=False)
 
-    def forward(self, locs, data=None, qlocs=None):
+    def forward(self, locs, data=None, qlocs=None, query_range=None, bounds=None):
+        """query_range / bounds: the two extensions of the product's ParticleCollision that the multi-GPU host
+        logic uses (tests/test_sharding_gloo.py drives that logic with these CPU modules)."""
         be = backend()
         ln = _np(locs)
-        low, gd = so.grid_bounds_torch(ln, self.radius, self.max_grid_dim)  # the reference's torch ops
+        if bounds is not None:
+            low, gd = _np(bounds[0]), _np(bounds[1])
+        else:
+            low, gd = so.grid_bounds_torch(ln, self.radius, self.max_grid_dim)  # the reference's torch ops
         if STABLE_ORDER:
             ids, idxs = so.COracle().hashgrid_order(ln, low, gd, self.radius, stable=True)
         else:
@@ -140,6 +145,8 @@ class ParticleCollision(torch.nn.Module):
         else:
             locs = self.reorder(idxs_t, locs)
         q = _np(locs) if qlocs is None else _np(qlocs)
+        if query_range is not None:
+            q = np.ascontiguousarray(_np(locs)[:, int(query_range[0]):int(query_range[1])])
         nb, _, _ = be.compute_collisions(q, _np(locs), low, gd, ids, self.radius, self.radius,
                                          self.max_collisions, self.include_self,
                                          self.max_grid_dim ** self.ndim)

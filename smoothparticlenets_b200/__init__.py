@@ -13,12 +13,12 @@ __init__.py:5-10).  Native code: libspnb.so (C ABI in include/spnb.h), built by
 from .kernels import KERNEL_NAMES, KERNEL_FN, DKERNEL_FN, KERNELS, DKERNELS  # noqa: F401
 from .convsp import ConvSP  # noqa: F401
 from .convsp_group import ConvSPGroup  # noqa: F401
-from .particlecollision import ParticleCollision, ReorderData, tile_lists_of, sym_flag_of  # noqa: F401
+from .particlecollision import ParticleCollision, ReorderData, tile_lists_of, sym_flag_of, grid_bounds  # noqa: F401
 from .convsdf import ConvSDF  # noqa: F401
 from .pbf import (pbf_stage1, pbf_stage2, pbf_stage3, pbf_integrate, pbf_velocity,  # noqa: F401
                   pbf_viscosity, fanout)
 from . import error_checking  # noqa: F401
 
 __all__ = ["ConvSP", "ConvSPGroup", "ConvSDF", "ParticleCollision", "ReorderData", "KERNEL_NAMES", "KERNEL_FN",
-           "DKERNEL_FN", "KERNELS", "DKERNELS", "tile_lists_of", "sym_flag_of", "pbf_stage1", "pbf_stage2", "pbf_stage3", "pbf_integrate",
+           "DKERNEL_FN", "KERNELS", "DKERNELS", "tile_lists_of", "sym_flag_of", "grid_bounds", "pbf_stage1", "pbf_stage2", "pbf_stage3", "pbf_integrate",
            "pbf_velocity", "pbf_viscosity", "fanout"]

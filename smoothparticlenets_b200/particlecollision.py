@@ -152,14 +152,16 @@ class ParticleCollision(torch.nn.Module):
             setattr(self, name, buf)
         return buf
 
-    def forward(self, locs, data=None, qlocs=None, query_range=None):
+    def forward(self, locs, data=None, qlocs=None, query_range=None, bounds=None):
         """Returns (locs, [data], idxs, neighbors) exactly as the reference
         (ParticleCollision.py:104-203): locs/data reordered by hash-grid cell, idxs[b,i] = original
         index of the particle now at i, neighbors BxMxK float lists terminated by -1.
 
         query_range=(start, end) is an extension for splitting ONE scene over several GPUs
         (scene_parallel.py): the queries are the reordered particles start..end-1 only, so neighbors
-        is Bx(end-start)xK -- the rows start..end-1 of what the call without it returns."""
+        is Bx(end-start)xK -- the rows start..end-1 of what the call without it returns.
+        bounds=(lower_bounds, grid_dims), both BxD, replaces the grid computed from `locs` (slab_parallel.py:
+        a rank that holds a slab of the scene hashes it on the WHOLE scene's grid)."""
         batch_size = locs.size()[0]
         N = locs.size()[1]
         ec.check_tensor_dims(locs, "locs", (batch_size, N, self.ndim))
@@ -189,11 +191,17 @@ class ParticleCollision(torch.nn.Module):
         with torch.no_grad(), torch.cuda.device(dev):
             st = nat.stream()
             ld = locs.detach()
-            lower_bounds = torch.empty(batch_size, D, device=dev, dtype=torch.float32)
-            grid_dims = torch.empty(batch_size, D, device=dev, dtype=torch.float32)
-            nat.check(L.spnb_grid_bounds(nat.ptr(ld), batch_size, N, D, float(self.radius), G,
-                                         nat.ptr(lower_bounds), nat.ptr(grid_dims), nat.ptr(ws),
-                                         ws_bytes, st), "spnb_grid_bounds")
+            if bounds is not None:
+                lower_bounds = nat.require_cuda_f32(bounds[0].contiguous(), "bounds[0]")
+                grid_dims = nat.require_cuda_f32(bounds[1].contiguous(), "bounds[1]")
+                ec.check_tensor_dims(lower_bounds, "bounds[0]", (batch_size, D))
+                ec.check_tensor_dims(grid_dims, "bounds[1]", (batch_size, D))
+            else:
+                lower_bounds = torch.empty(batch_size, D, device=dev, dtype=torch.float32)
+                grid_dims = torch.empty(batch_size, D, device=dev, dtype=torch.float32)
+                nat.check(L.spnb_grid_bounds(nat.ptr(ld), batch_size, N, D, float(self.radius), G,
+                                             nat.ptr(lower_bounds), nat.ptr(grid_dims), nat.ptr(ws),
+                                             ws_bytes, st), "spnb_grid_bounds")
             idxs = torch.empty(batch_size, N, device=dev, dtype=torch.float32)
             nat.check(L.spnb_hashgrid_order(nat.ptr(ld), nat.ptr(lower_bounds), nat.ptr(grid_dims),
                                             nat.ptr(cellIDs), nat.ptr(idxs), nat.ptr(ws), ws_bytes,
@@ -248,3 +256,20 @@ class ParticleCollision(torch.nn.Module):
         if has_data:
             return locs, data, idxs, neighbors
         return locs, idxs, neighbors
+
+
+def grid_bounds(locs, radius, max_grid_dim):
+    """(lower_bounds, grid_dims), both BxD, of ParticleCollision's hash grid for `locs` BxNxD -- the fp32 torch
+    CPU arithmetic of the reference (ParticleCollision.py:174-181), bit for bit, on the device."""
+    nat.require_cuda_f32(locs, "locs")
+    locs = locs.contiguous()
+    B, N, D = locs.shape
+    L = nat.lib()
+    wsb = L.spnb_hashgrid_workspace_bytes(B, N, D, max_grid_dim)
+    with torch.no_grad(), torch.cuda.device(locs.device):
+        ws = torch.empty((wsb + 3) // 4, device=locs.device, dtype=torch.float32)
+        low = torch.empty(B, D, device=locs.device, dtype=torch.float32)
+        gd = torch.empty(B, D, device=locs.device, dtype=torch.float32)
+        nat.check(L.spnb_grid_bounds(nat.ptr(locs), B, N, D, float(radius), int(max_grid_dim), nat.ptr(low),
+                                     nat.ptr(gd), nat.ptr(ws), wsb, nat.stream()), "spnb_grid_bounds")
+    return low, gd

@@ -1,0 +1,213 @@
+"""One scene over several GPUs as SPATIAL SLABS (BASELINE.json config 5): positions are sharded.
+
+Every rank starts with an arbitrary share of the scene's particles.  The decomposition relies on the cell hash being
+row-major with grid dimension 0 most significant (common_funcs.h:107-119): a contiguous block of dim-0 cell LAYERS is
+a contiguous block of the global cell-sorted order, so a rank that owns a block of layers can reproduce its part of
+the global neighbour search from its own particles plus one layer of its neighbours' -- bit for bit.
+
+  1. bounds     all-reduce(min / max) of the coordinates (2 D floats) -> the SAME grid on every rank;
+  2. layers     histogram of the particles over dim-0 layers, all-reduce(sum); cuts that balance the counts give
+                each rank a block of layers [cut_r, cut_r+1);
+  3. buckets    all_to_all of (position, data, global id) rows: every particle moves to the owner of its layer;
+  4. halo       the first / last layer of every rank is copied to the previous / next rank (positions + ids);
+  5. search     the extended set [left halo | own | right halo], ordered by global id, goes through the ordinary
+                ParticleCollision with the global bounds and query_range = the own block: same cell keys, same
+                stable order, hence the own rows equal the single-GPU rows up to a constant index shift;
+  6. layers     ConvSP on the own queries: per input, the halo rows of the features travel the same two links
+                (forward), and the gradients of borrowed rows -- d/d(data) and d/d(locs) -- travel back and are
+                added by their owner (backward), all inside autograd Functions.
+
+Memory per rank is (N / world + two layers) rows; nothing is replicated.  The exchange steps are NCCL collectives /
+send-recv pairs over NVLink (gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+from .scene_parallel import HaloPlan, _HaloRows
+
+
+class _AllToAllRows(torch.autograd.Function):
+    """rows [n, W] split by `send` counts -> rows received from every rank (`recv` counts); backward: the reverse."""
+
+    @staticmethod
+    def forward(ctx, x, send, recv, group):
+        ctx.send, ctx.recv, ctx.group = send, recv, group
+        out = x.new_empty(sum(recv), x.shape[1])
+        dist.all_to_all_single(out, x.contiguous(), recv, send, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out = g.new_empty(sum(ctx.send), g.shape[1])
+        dist.all_to_all_single(out, g.contiguous(), ctx.send, ctx.recv, group=ctx.group)
+        return out, None, None, None
+
+
+def _swap_rows(outs, ins, group):
+    ops = []
+    for peer, t, is_send in sorted(outs + ins, key=lambda p: (p[0], p[2])):
+        ops.append(dist.P2POp(dist.isend if is_send else dist.irecv, t, peer, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def layer_cuts(counts, world):
+    """counts: particles per dim-0 layer (list).  Returns world+1 non-decreasing layer indices, cut[r] <= layers of
+    rank r < cut[r+1], balancing the particle counts; every rank gets at least one layer when there are enough."""
+    L = len(counts)
+    total = float(sum(counts))
+    cuts = [0]
+    acc, layer = 0.0, 0
+    for r in range(1, world):
+        target = total * r / world
+        while layer < L and acc + counts[layer] / 2.0 <= target:
+            acc += counts[layer]
+            layer += 1
+        lo = cuts[-1] + 1 if L >= world else cuts[-1]
+        hi = L - (world - r) if L >= world else L
+        cuts.append(min(max(layer, lo), max(hi, lo)))
+        # keep the running sum consistent with the (possibly adjusted) cut
+        acc = float(sum(counts[:cuts[-1]]))
+        layer = cuts[-1]
+    cuts.append(L)
+    return cuts
+
+
+class SlabScene(object):
+    """Neighbour search and ConvSP for the slab of one scene owned by this rank (batch size 1).
+
+        scene = SlabScene(coll, bounds_fn)                 # coll: ParticleCollision of the scene's radius
+        own_locs, own_data, own_gid, nbrs = scene.collide(locs_local, gid_local, data_local)
+        out_own = scene.convsp(conv, data_own)             # rows in the own (cell-sorted) order
+        back = scene.to_origin(out_own)                    # rows back where (and in the order) they came from
+
+    `bounds_fn(minmax [1, 2, D]) -> (lower_bounds [1, D], grid_dims [1, D])` must be the grid-bounds computation of the
+    single-GPU path (spnb_grid_bounds on the two extreme points gives exactly that).
+    """
+
+    def __init__(self, coll, bounds_fn, group=None):
+        self.coll, self.bounds_fn, self.group = coll, bounds_fn, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    # ---- steps 1-5 --------------------------------------------------------------------------------------
+    def collide(self, locs, gid, data=None):
+        """locs [1, n, D] (this rank's share, any order), gid [n] int64 global particle ids, data [1, n, C]."""
+        if locs.shape[0] != 1:
+            raise ValueError("SlabScene handles one scene (batch size 1)")
+        dev, D = locs.device, locs.shape[2]
+        R, g = self.world, self.group
+        radius = float(self.coll.radius)
+        # 1. the global grid
+        mm = torch.stack([locs.detach()[0].min(0).values, -locs.detach()[0].max(0).values])
+        dist.all_reduce(mm, op=dist.ReduceOp.MIN, group=g)
+        minmax = torch.stack([mm[0], -mm[1]]).unsqueeze(0).contiguous()
+        low, gd = self.bounds_fn(minmax)
+        self.bounds = (low, gd)
+        # 2. dim-0 layer of every particle: the cell coordinate of loc2grid / partial_grid_hash
+        nlayers = int(gd[0, 0].item())
+        if nlayers < 1:
+            raise ValueError("degenerate grid: all particles share their first coordinate")
+        rt = torch.full((), radius, device=dev, dtype=torch.float32)
+        layer = torch.trunc((locs.detach()[0, :, 0] - low[0, 0]) / rt).clamp_(0, nlayers - 1).to(torch.int64)
+        hist = torch.bincount(layer, minlength=nlayers).to(torch.int64)
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=g)
+        cuts = layer_cuts(hist.tolist(), R)               # host sync: R+1 numbers decide the decomposition
+        self.cuts = cuts
+        cut_t = torch.tensor(cuts[1:-1], device=dev, dtype=torch.int64)
+        # 3. bucket exchange
+        dest = torch.bucketize(layer, cut_t, right=True)
+        order = torch.argsort(dest, stable=True)
+        send = torch.bincount(dest, minlength=R).tolist()
+        recv_t = torch.empty(R, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv_t, torch.tensor(send, device=dev, dtype=torch.int64), group=g)
+        recv = recv_t.tolist()
+        self._a2a = (order, send, recv, locs.shape[1])
+        C = 0 if data is None else data.shape[2]
+        cols = [locs[0]] + ([data[0]] if data is not None else [])
+        rows = torch.cat(cols, 1)[order]
+        got = _AllToAllRows.apply(rows, send, recv, g)
+        own_gid = torch.empty(sum(recv), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(own_gid, gid[order].contiguous(), recv, send, group=g)
+        own_layer = torch.empty(sum(recv), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(own_layer, layer[order].contiguous(), recv, send, group=g)
+        # own block in global-id order (the stable sort by cell then reproduces the global order inside every cell)
+        by_gid = torch.argsort(own_gid)
+        got, own_gid, own_layer = got[by_gid], own_gid[by_gid], own_layer[by_gid]
+        self._by_gid = by_gid
+        m = got.shape[0]
+        # 4. halo of positions: my first layer -> previous rank, my last layer -> next rank
+        first_mask = own_layer == cuts[self.rank]
+        last_mask = own_layer == cuts[self.rank + 1] - 1
+        has_prev = self.rank > 0 and cuts[self.rank] > 0
+        has_next = self.rank < R - 1 and cuts[self.rank + 1] < nlayers
+        nfirst, nlast = int(first_mask.sum().item()), int(last_mask.sum().item())
+        sizes = torch.tensor([nfirst, nlast], device=dev, dtype=torch.int64)
+        every = [torch.empty_like(sizes) for _ in range(R)]
+        dist.all_gather(every, sizes, group=g)
+        nl = int(every[self.rank - 1][1].item()) if has_prev else 0     # previous rank's last layer
+        nr = int(every[self.rank + 1][0].item()) if has_next else 0     # next rank's first layer
+        pos = got[:, :D].detach()
+        outs, ins = [], []
+        left = torch.empty(nl, D + 1, device=dev, dtype=torch.float64)
+        right = torch.empty(nr, D + 1, device=dev, dtype=torch.float64)
+        pack = lambda mask: torch.cat([pos[mask].double(), own_gid[mask].double().unsqueeze(1)], 1).contiguous()
+        if has_prev:
+            outs.append((self.rank - 1, pack(first_mask), True))
+            ins.append((self.rank - 1, left, False))
+        if has_next:
+            outs.append((self.rank + 1, pack(last_mask), True))
+            ins.append((self.rank + 1, right, False))
+        _swap_rows(outs, ins, g)
+        # 5. the extended set in global-id order -> ParticleCollision with the global bounds
+        ext_pos = torch.cat([left[:, :D].float(), pos, right[:, :D].float()], 0)
+        ext_gid = torch.cat([left[:, D].long(), own_gid, right[:, D].long()], 0)
+        eorder = torch.argsort(ext_gid)
+        ext_sorted_in = ext_pos[eorder].unsqueeze(0).contiguous()
+        res = self.coll(ext_sorted_in, query_range=(nl, nl + m), bounds=(low, gd))
+        ext_locs, idxs, neighbors = res[0], res[-2], res[-1]
+        perm = eorder[idxs[0].long()]                    # cell-sorted position -> index into [left | own | right]
+        # own rows, now in cell-sorted order: positions nl .. nl+m of the sorted extended set
+        own_sel = perm[nl:nl + m] - nl                   # index into the own block (gid order)
+        self._own_sel = own_sel
+        self.nl, self.m, self.nr = nl, m, nr
+        self.neighbors = neighbors
+        self.own_gid = own_gid[own_sel]
+        # the first / last own layers are contiguous at the ends of the own block in the sorted order
+        self.plan = HaloPlan(nl + m + nr, nl, nl + m,
+                             sends=([(self.rank - 1, nl, nl + nfirst)] if has_prev else []) +
+                                   ([(self.rank + 1, nl + m - nlast, nl + m)] if has_next else []),
+                             recvs=([(self.rank - 1, 0, nl)] if has_prev else []) +
+                                   ([(self.rank + 1, nl + m, nl + m + nr)] if has_next else []),
+                             group=g)
+        own_rows = got[own_sel]                          # differentiable: through the all_to_all back to the inputs
+        self.own_locs = own_rows[:, :D].unsqueeze(0)
+        own_data = own_rows[:, D:D + C].unsqueeze(0) if C else None
+        return self.own_locs, own_data, self.own_gid, neighbors
+
+    # ---- step 6 -------------------------------------------------------------------------------------------
+    def extended(self, x_own):
+        """[1, m, C] own rows (cell-sorted) -> [1, nl + m + nr, C] with the two halo layers filled in; the
+        gradients of the halo rows return to their owners in backward."""
+        return _HaloRows.apply(x_own.contiguous(), self.plan)
+
+    def convsp(self, conv, data_own, locs_own=None):
+        locs_own = self.own_locs if locs_own is None else locs_own
+        locs_ext = self.extended(locs_own)
+        data_ext = self.extended(data_own)
+        return conv(locs_ext, data_ext, self.neighbors, qlocs=locs_ext[:, self.nl:self.nl + self.m])
+
+    def to_origin(self, x_own):
+        """[1, m, C] rows in the own order -> [1, n, C] rows of the particles this rank contributed, in the order
+        it contributed them (the inverse of steps 3-5; differentiable)."""
+        order, send, recv, n = self._a2a
+        inv_sel = torch.empty_like(self._own_sel)
+        inv_sel[self._own_sel] = torch.arange(self.m, device=x_own.device)
+        rows = x_own[0][inv_sel]                         # gid order
+        inv_gid = torch.empty_like(self._by_gid)
+        inv_gid[self._by_gid] = torch.arange(self.m, device=x_own.device)
+        rows = rows[inv_gid]                             # arrival order of the all_to_all
+        back = _AllToAllRows.apply(rows, recv, send, self.group)
+        out = torch.empty_like(back)
+        out[order] = back
+        return out.unsqueeze(0)

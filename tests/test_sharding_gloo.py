@@ -138,3 +138,101 @@ def test_halo_exchange_matches_single_process_on_three_ranks():
     for rank in range(world):
         same_rows, same_grads, halo = res[rank]
         assert same_rows and same_grads, (rank, res[rank])
+
+
+# ---- spatial slabs: positions sharded (smoothparticlenets_b200/slab_parallel.py) ------------------------------
+def _slab_case():
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    N, D, C, O, R = 900, 3, 2, 3, 0.1
+    r = cases.rng(12)
+    locs = (r.rand(1, N, D) * np.array([1.3, 0.5, 0.5])).astype(np.float32)   # ~13 cell layers along dim 0
+    data = r.rand(1, N, C).astype(np.float32)
+    w = r.rand(O, C, 1).astype(np.float32)
+    go = r.rand(1, N, O).astype(np.float32)
+    return N, D, C, O, R, locs, data, w, go
+
+
+def _slab_modules(R, C, O, D, w):
+    from oracle import cpu_modules as cm
+    from oracle import spn_oracle as so
+    coll = cm.ParticleCollision(D, R, max_collisions=64, include_self=False)
+    conv = cm.ConvSP(C, O, D, 1, 1, R, kernel_fn="spiky", with_params=False)
+    with torch.no_grad():
+        conv.weight.copy_(torch.from_numpy(w))
+    bounds_fn = lambda mm: tuple(torch.from_numpy(a) for a in so.grid_bounds_torch(mm.numpy(), R, coll.max_grid_dim))
+    return cm, coll, conv, bounds_fn
+
+
+def _slab_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from oracle import cpu_modules as cm
+    cm.STABLE_ORDER = True   # the product's stable order (ties by ascending index), which the decomposition relies on
+    from smoothparticlenets_b200.slab_parallel import SlabScene
+    N, D, C, O, R, locs, data, w, go = _slab_case()
+    _, coll, conv, bounds_fn = _slab_modules(R, C, O, D, w)
+    # an arbitrary initial distribution: particle i starts on rank (7 i) % world
+    mine = np.array([i for i in range(N) if (7 * i) % world == rank])
+    lt = torch.from_numpy(locs[:, mine]).requires_grad_(True)
+    dt = torch.from_numpy(data[:, mine]).requires_grad_(True)
+    scene = SlabScene(coll, bounds_fn)
+    own_locs, own_data, own_gid, nbrs = scene.collide(lt, torch.from_numpy(mine), dt)
+    out_own = scene.convsp(conv, own_data)
+    out_back = scene.to_origin(out_own)
+    out_back.backward(torch.from_numpy(go[:, mine]))
+    ret[rank] = dict(mine=mine, gid=own_gid.numpy(), nbrs=nbrs.numpy(), nl=scene.nl, m=scene.m, cuts=scene.cuts,
+                     out=out_back.detach().numpy(), dlocs=lt.grad.numpy(), ddata=dt.grad.numpy(),
+                     own_locs=own_locs.detach().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_decomposition_matches_single_process_on_three_ranks():
+    """Positions sharded over 3 ranks (bucket exchange, halo layers, local search on the global grid): the own
+    neighbour rows equal the single-process rows up to the block's index shift, outputs and the gradients that
+    come back to the particles' original owners equal the single-process ones."""
+    world = 3
+    port = 33500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_slab_worker, args=(world, port, ret), nprocs=world, join=True)
+        res = dict(ret)
+    from oracle import cpu_modules as cm
+    cm.STABLE_ORDER = True
+    try:
+        N, D, C, O, R, locs, data, w, go = _slab_case()
+        _, coll, conv, _ = _slab_modules(R, C, O, D, w)
+        lt = torch.from_numpy(locs).requires_grad_(True)
+        dt = torch.from_numpy(data).requires_grad_(True)
+        sl, sd, idxs, nb = coll(lt, dt)
+        out = conv(sl, sd, nb)
+        back = cm.ReorderData(reverse=True)(idxs, out)
+        back.backward(torch.from_numpy(go))
+    finally:
+        cm.STABLE_ORDER = False
+    gidx = idxs[0].numpy().astype(np.int64)          # sorted position -> global id
+    nbh = nb[0].numpy()
+    start = 0
+    assert sum(res[r]["m"] for r in range(world)) == N
+    for r in range(world):
+        d = res[r]
+        m, nl = d["m"], d["nl"]
+        assert m > 0 and d["cuts"] == res[0]["cuts"]
+        # the own block is the next m particles of the global cell-sorted order ...
+        assert np.array_equal(d["gid"], gidx[start:start + m])
+        assert np.array_equal(d["own_locs"][0], sl[0].detach().numpy()[start:start + m])
+        # ... and its rows are the global rows shifted by (start - nl)
+        want = nbh[start:start + m]
+        shifted = np.where(want >= 0, want - (start - nl), -1)
+        assert np.array_equal(d["nbrs"][0], shifted)
+        np.testing.assert_allclose(d["out"][0], back[0].detach().numpy()[d["mine"]], rtol=1e-6, atol=1e-6)
+        # gradients of rows lent to a neighbour rank come back over the halo link and are added last: the same
+        # terms in another order (fp32)
+        gl, gdt = lt.grad[0].numpy(), dt.grad[0].numpy()
+        np.testing.assert_allclose(d["dlocs"][0], gl[d["mine"]], rtol=1e-4, atol=1e-6 * np.abs(gl).max())
+        np.testing.assert_allclose(d["ddata"][0], gdt[d["mine"]], rtol=1e-4, atol=1e-6 * np.abs(gdt).max())
+        start += m
