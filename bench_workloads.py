@@ -74,6 +74,10 @@ def run_c3(args, ClockSampler):
     ms = _time_steps(torch, fwd, args.steps, args.warmup, torch.cuda.synchronize)
     launches = (nat.lib().spnb_launch_count() - n0) // (args.steps + max(3, args.warmup)) * args.steps
     clk = clocks.stop()
+    # the contraction kernels alone (library knob: skips the gather, multiplies whatever the image buffer holds)
+    os.environ["SPNB_WIDE_GEMM_ONLY"] = "1"
+    ms_gemm = _time_steps(torch, fwd, args.steps, 1, torch.cuda.synchronize) / args.steps
+    del os.environ["SPNB_WIDE_GEMM_ONLY"]
     # e2e: host positions / features / lists in, output out, every step
     hq, hl, hd, hn = (t.cpu().pin_memory() for t in (q, sl, sd, nb))
     ho = torch.empty(out.shape).pin_memory()
@@ -101,11 +105,16 @@ def run_c3(args, ClockSampler):
         "e2e": {"value": M / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": sum(t.numel() * 4 for t in (hq, hl, hd, hn)), "d2h_bytes_per_step": ho.numel() * 4},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "k_convsp_wide_mma_fwd", "achieved": flops / (t_ms * 1e-3) / 1e12,
-                     "peak": tf32_peak / 3.0, "unit": "TFLOP/s", "frac": flops / (t_ms * 1e-3) / 1e12 / (tf32_peak / 3.0),
+        # the contraction (k_wide_gemm + weight images): 3 TF32 MMAs per product; it streams the A operand images
+        # (2 x 32 KB per 128 queries and kernel cell) from HBM, which is what bounds it
+        "roofline": {"bound": "tensor", "kernel": "k_wide_gemm", "achieved": flops / (ms_gemm * 1e-3) / 1e12,
+                     "peak": tf32_peak / 3.0, "unit": "TFLOP/s", "frac": flops / (ms_gemm * 1e-3) / 1e12 / (tf32_peak / 3.0),
                      "traffic": None, "peak_source": src + ": bf16 dense / 2 (TF32) / 3 (3xTF32 products)",
-                     "note": "dense-contraction FLOPs only (2*ncells*C*O per query); the kernel's time is dominated by "
-                             "the CUDA-core gather phase that builds the A operand, see DESIGN.md"},
+                     "ms_per_launch_set": ms_gemm, "share_of_step": ms_gemm / t_ms,
+                     "hbm_gbs_of_operand_stream": (M * ncells * C * 8.0) / (ms_gemm * 1e-3) / 1e9, "hbm_peak_gbs": hbm,
+                     "note": "dense-contraction FLOPs (2*ncells*C*O per query) over the time of the contraction kernels "
+                             "alone; the step is dominated by the CUDA-core gather (k_wide_gather) that builds the A "
+                             "operand: %.1f %% of the step" % (100.0 * (1.0 - ms_gemm / t_ms))},
     }
     print(json.dumps(line))
 
