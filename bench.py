@@ -438,7 +438,8 @@ def run_ours(args):
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(top, {}).get("dram_bytes_per_launch")
         t_ms, cnt, byts = kern[top]
-        achieved = byts / (t_ms * 1e-3) / 1e9
+        own = reduced.get(top, byts)          # the op's OWN compulsory bytes (fused ops: inputs / outputs of the
+        achieved = own / (t_ms * 1e-3) / 1e9  # fused op itself, not of the layers it replaces)
         step_bytes = fluidstep.algorithmic_bytes_per_particle_step(nbar) * B * N
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -454,18 +455,24 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(per_step_launches * args.steps),
+            # dominant op of the step (largest share of its device time), on its OWN compulsory bytes
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": byts, "ms_per_launch": t_ms,
+                         "algorithmic_bytes_per_launch": own, "ms_per_launch": t_ms,
                          "share_of_step": shares[top] / sum(shares.values()),
-                         "bytes_definition": ("SURVEY.md 8(d) per-layer bytes summed over the layers the fused op "
-                                              "replaces (pack pre-pass + list walk timed together)" if fused else
+                         "bytes_definition": ("the fused op's own compulsory bytes: positions, distinct data tensors and "
+                                              "the lists read once, grad_out read once, every output written once "
+                                              "(pack pre-pass + tile kernel timed together)" if fused else
                                               "SURVEY.md 8(d) per-layer bytes"),
-                         "achieved_own_bytes": (reduced[top] / (t_ms * 1e-3) / 1e9) if top in reduced else None},
+                         # the same time against the SURVEY.md 8(d) bytes of the per-layer calls the op replaces
+                         "frac_vs_unfused": (byts / (t_ms * 1e-3) / 1e9 / peak) if top in reduced else None},
+            # the whole step against the sum of the SURVEY.md 8(d) bytes of its 29 ConvSP fwd+bwd, search and reorders
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes,
                               "achieved_gbs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
                               "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
-            "kernels": {k: {"ms": round(v[0], 4), "per_step": v[1], "gbs": round(v[2] / (v[0] * 1e-3) / 1e9, 1)}
+            "kernels": {k: {"ms": round(v[0], 4), "per_step": v[1],
+                            "gbs_own": round(reduced.get(k, v[2]) / (v[0] * 1e-3) / 1e9, 1),
+                            "frac_own": round(reduced.get(k, v[2]) / (v[0] * 1e-3) / 1e9 / peak, 4)}
                         for k, v in kern.items()},
             "eager_ms_per_step": ms_eager,
         }
