@@ -246,6 +246,21 @@ int spnb_convsdf_backward(const float* locs, int batch_size, int N, int ndims, c
                           float max_distance, const float* grad_out, float* dlocs, float* dweight,
                           float* dposes, void* stream);
 
+/* Same as spnb_convsdf_backward, and additionally fills the rotation columns of dposes with the
+ * analytic derivative of the forward formula (rotate_point, common_funcs.h:203-235) with respect to
+ * the 2-D angle / the four quaternion components taken as independent variables.  The reference
+ * has no counterpart: it estimates these columns with forward differences (eps = 1e-3,
+ * convsdf.py:211-224), which costs M * R extra forward passes.  Opt-in through
+ * ConvSDF(compute_pose_grads="analytic"). */
+int spnb_convsdf_backward_analytic(const float* locs, int batch_size, int N, int ndims,
+                                   const float* idxs, const float* poses, const float* scales, int M,
+                                   int pose_len, const float* sdfs, size_t sdfs_len,
+                                   const float* sdf_offsets, const float* sdf_shapes, int nsdfs,
+                                   const float* weight, int nkernels, int ncells,
+                                   const float* kernel_size, const float* dilation,
+                                   float max_distance, const float* grad_out, float* dlocs,
+                                   float* dweight, float* dposes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

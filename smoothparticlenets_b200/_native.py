@@ -51,6 +51,9 @@ _SIGNATURES = {
                                   _vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "spnb_convsdf_backward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp, _i, _vp,
                                    _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),
+    "spnb_convsdf_backward_analytic": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp,
+                                            _vp, _i, _vp, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp,
+                                            _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

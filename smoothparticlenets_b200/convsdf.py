@@ -6,6 +6,10 @@ packing (flat atlas + exclusive-cumsum offsets + [dims..., cell_size] shape rows
 -- iff compute_pose_grads -- poses; none for idxs / scales, convsdf.py:226-233).  As in the
 reference, the rotation components of the pose gradient are forward finite differences with
 eps = 1e-3 evaluated in Python (convsdf.py:211-224); the translation components are analytic.
+
+Extension: ``compute_pose_grads="analytic"`` computes the rotation components in the backward
+kernel as well (exact derivative of the forward formula with respect to the 2-D angle / the four
+quaternion components as independent variables), which removes the M * R extra forward passes.
 """
 import numbers  # noqa: F401
 
@@ -48,7 +52,9 @@ class ConvSDF(torch.nn.Module):
         else:
             self.register_buffer("weight", weight)
             self.register_buffer("bias", bias)
-        self.compute_pose_grads = bool(compute_pose_grads)
+        # True: the reference's recipe (finite-difference rotation columns); "analytic": in-kernel.
+        self.compute_pose_grads = ("analytic" if compute_pose_grads == "analytic"
+                                   else bool(compute_pose_grads))
         self._kernel_size = ec.list2tensor(self._kernel_size)
         self._dilation = ec.list2tensor(self._dilation)
         self.register_buffer("kernel_size", self._kernel_size)
@@ -129,15 +135,17 @@ class _ConvSDFFunction(torch.autograd.Function):
         dl = torch.empty_like(locs) if need_l else None
         dw = torch.empty_like(weight) if need_w else None
         dp = torch.empty_like(poses) if need_p else None
+        analytic = ctx.compute_pose_grads == "analytic"
         if need_l or need_w or need_p:
+            fn = "spnb_convsdf_backward_analytic" if analytic else "spnb_convsdf_backward"
             with torch.cuda.device(dev):
-                nat.check(nat.lib().spnb_convsdf_backward(
+                nat.check(getattr(nat.lib(), fn)(
                     nat.ptr(locs), B, N, D, nat.ptr(idxs), nat.ptr(poses), nat.ptr(scales), S,
                     poses.shape[2], nat.ptr(sdfs), sdfs.numel(), nat.ptr(offs), nat.ptr(shapes),
                     shapes.shape[0], nat.ptr(weight), O, ncells, nat.ptr(ksize), nat.ptr(dil),
                     ctx.max_distance, nat.ptr(grad_output), nat.ptr(dl), nat.ptr(dw), nat.ptr(dp),
-                    nat.stream()), "spnb_convsdf_backward")
-        if need_p and poses.shape[2] > D:
+                    nat.stream()), fn)
+        if need_p and poses.shape[2] > D and not analytic:
             # Rotation components by forward differences, as the reference does
             # (convsdf.py:211-224): eps = 1e-3, one extra forward per (object, component).
             args = (scales, weight, bias, sdfs, offs, shapes, ksize, dil, ctx.max_distance)

@@ -67,6 +67,41 @@ __device__ __forceinline__ void rotate_vec(float* p, const float* rot, bool inve
     }
 }
 
+// Vector part of conj(l) * (0,v) * r for quaternions stored xyzw.  rotate_point's inverse rotation
+// is B(r, r, v); it is bilinear in (l, r), which is what the analytic pose gradient differentiates.
+__device__ __forceinline__ void quat_sandwich(const float* l, const float* r, const float* v, float* o)
+{
+    const float aw = -v[0] * r[0] - v[1] * r[1] - v[2] * r[2];
+    const float ax = v[0] * r[3] + v[1] * r[2] - v[2] * r[1];
+    const float ay = v[1] * r[3] + v[2] * r[0] - v[0] * r[2];
+    const float az = v[2] * r[3] + v[0] * r[1] - v[1] * r[0];
+    o[0] = l[3] * ax - l[0] * aw - l[1] * az + l[2] * ay;
+    o[1] = l[3] * ay - l[1] * aw - l[2] * ax + l[0] * az;
+    o[2] = l[3] * az - l[2] * aw - l[0] * ay + l[1] * ax;
+}
+
+// d value / d rotation parameters of the object that owns a kernel cell, given the gradient `gl` of
+// the value in the object's frame, the frame point `pl` and the world offset `d` = point - t.
+// The parameters are differentiated as they enter rotate_point (common_funcs.h:203-235): the 2-D
+// angle, or the four quaternion components as independent variables (no renormalisation).
+template <int D>
+__device__ __forceinline__ void rotation_grad(const float* rot, const float* gl, const float* pl,
+                                              const float* d, float* out)
+{
+    if (D == 2) {
+        out[0] = gl[0] * pl[1] - gl[1] * pl[0];
+    } else if (D == 3) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float e[4] = {0.0f, 0.0f, 0.0f, 0.0f}, u[3], w[3];
+            e[k] = 1.0f;
+            quat_sandwich(e, rot, d, u);
+            quat_sandwich(rot, e, d, w);
+            out[k] = gl[0] * (u[0] + w[0]) + gl[1] * (u[1] + w[1]) + gl[2] * (u[2] + w[2]);
+        }
+    }
+}
+
 // rec_nlinear_interp (common_funcs.h:327-362) unrolled at compile time.  `grad` (if GRAD) receives
 // d value / d frac per dimension.
 template <int D, int DIM, bool GRAD>
@@ -160,12 +195,12 @@ k_convsdf(const float* __restrict__ locs, int N, const float* __restrict__ idxs,
           const float* __restrict__ weight, const float* __restrict__ bias, int O, int ncells,
           const float* __restrict__ ksize, const float* __restrict__ dilation, float max_distance,
           float* __restrict__ out, const float* __restrict__ go, float* __restrict__ dlocs,
-          float* dweight, float* dposes, int dw_in_smem)
+          float* dweight, float* dposes, int dw_in_smem, int rot_grads)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     ObjRec<D>* recs = reinterpret_cast<ObjRec<D>*>(s_raw);
     float* s_dw = reinterpret_cast<float*>(recs + S);  // [O*ncells] if dw_in_smem
-    float* s_dp = s_dw + (dw_in_smem ? O * ncells : 0); // [S*D] if dposes
+    float* s_dp = s_dw + (dw_in_smem ? O * ncells : 0); // [S*pose_len] if dposes
     const int b = blockIdx.y;
     const int n = blockIdx.x * kSdfThreads + threadIdx.x;
 
@@ -198,7 +233,7 @@ k_convsdf(const float* __restrict__ locs, int N, const float* __restrict__ idxs,
         if (dw_in_smem)
             for (int i = threadIdx.x; i < O * ncells; i += kSdfThreads) s_dw[i] = 0.0f;
         if (dposes)
-            for (int i = threadIdx.x; i < S * D; i += kSdfThreads) s_dp[i] = 0.0f;
+            for (int i = threadIdx.x; i < S * pose_len; i += kSdfThreads) s_dp[i] = 0.0f;
     }
     __syncthreads();
 
@@ -262,11 +297,11 @@ k_convsdf(const float* __restrict__ locs, int N, const float* __restrict__ idxs,
                 float pt[D];
 #pragma unroll
                 for (int i = 0; i < D; ++i) pt[i] = x[i] + (kidx[i] - half[i]) * dil[i];
-                float best = max_distance;
+                float best = max_distance, coef = 0.0f;
                 int best_m = -1;
-                float best_g[D];
+                float best_g[D], best_gl[D], best_pl[D];
 #pragma unroll
-                for (int i = 0; i < D; ++i) best_g[i] = 0.0f;
+                for (int i = 0; i < D; ++i) best_g[i] = best_gl[i] = best_pl[i] = 0.0f;
                 for (int m = 0; m < S; ++m) {
                     if (!((live[m >> 5] >> (m & 31)) & 1u)) continue;
                     const ObjRec<D>& r = recs[m];
@@ -279,7 +314,11 @@ k_convsdf(const float* __restrict__ locs, int N, const float* __restrict__ idxs,
                         best_m = m;
                         if (BWD) {
 #pragma unroll
-                            for (int i = 0; i < D; ++i) g[i] *= r.scale;
+                            for (int i = 0; i < D; ++i) {
+                                g[i] *= r.scale;
+                                best_gl[i] = g[i];
+                                best_pl[i] = p[i];
+                            }
                             rotate_vec<D>(g, r.rot, false);
 #pragma unroll
                             for (int i = 0; i < D; ++i) best_g[i] = g[i];
@@ -301,10 +340,22 @@ k_convsdf(const float* __restrict__ locs, int N, const float* __restrict__ idxs,
 #pragma unroll
                             for (int i = 0; i < D; ++i) {
                                 a_dl[i] += best_g[i] * g_o[o] * w;
-                                if (dposes && best_m >= 0) atomicAdd(&s_dp[best_m * D + i], -best_g[i] * g_o[o] * w);
+                                if (dposes && best_m >= 0)
+                                    atomicAdd(&s_dp[best_m * pose_len + i], -best_g[i] * g_o[o] * w);
                             }
+                            coef += g_o[o] * w;
                         }
                     }
+                }
+                if (BWD && D > 1 && rot_grads && dposes && best_m >= 0) {
+                    const ObjRec<D>& r = recs[best_m];
+                    float d[D], dr[D == 3 ? 4 : 1];
+#pragma unroll
+                    for (int i = 0; i < D; ++i) d[i] = pt[i] - r.t[i];
+                    rotation_grad<D>(r.rot, best_gl, best_pl, d, dr);
+#pragma unroll
+                    for (int i = 0; i < (D == 3 ? 4 : 1); ++i)
+                        atomicAdd(&s_dp[best_m * pose_len + D + i], dr[i] * coef);
                 }
                 ++kidx[0];
 #pragma unroll
@@ -330,9 +381,9 @@ k_convsdf(const float* __restrict__ locs, int N, const float* __restrict__ idxs,
                 if (v != 0.0f) atomicAdd(dweight + i, v);
             }
         if (dposes)
-            for (int i = threadIdx.x; i < S * D; i += kSdfThreads) {
+            for (int i = threadIdx.x; i < S * pose_len; i += kSdfThreads) {
                 const float v = s_dp[i];
-                if (v != 0.0f) atomicAdd(dposes + ((size_t)b * S + i / D) * pose_len + i % D, v);
+                if (v != 0.0f) atomicAdd(dposes + (size_t)b * S * pose_len + i, v);
             }
     }
 }
@@ -344,7 +395,7 @@ static int launch_convsdf(const float* locs, int B, int N, const float* idxs, co
                           int nsdfs, const float* weight, const float* bias, int O, int ncells,
                           const float* ksize, const float* dil, float max_distance, float* out,
                           const float* go, float* dlocs, float* dweight, float* dposes,
-                          cudaStream_t stream)
+                          int rot_grads, cudaStream_t stream)
 {
     size_t smem = sizeof(ObjRec<D>) * (size_t)S;
     int dw_in_smem = 0;
@@ -353,7 +404,7 @@ static int launch_convsdf(const float* locs, int B, int N, const float* idxs, co
             dw_in_smem = 1;
             smem += sizeof(float) * (size_t)O * ncells;
         }
-        if (dposes) smem += sizeof(float) * (size_t)S * D;
+        if (dposes) smem += sizeof(float) * (size_t)S * pose_len;
         if (dweight) cudaMemsetAsync(dweight, 0, sizeof(float) * (size_t)O * ncells, stream);
         if (dposes) cudaMemsetAsync(dposes, 0, sizeof(float) * (size_t)B * S * pose_len, stream);
     }
@@ -363,7 +414,7 @@ static int launch_convsdf(const float* locs, int B, int N, const float* idxs, co
     k_convsdf<D, BWD><<<grid, kSdfThreads, smem, stream>>>(
         locs, N, idxs, poses, scales, S, pose_len, sdfs, (long long)sdfs_len, sdf_offsets,
         sdf_shapes, nsdfs, weight, bias, O, ncells, ksize, dil, max_distance, out, go, dlocs,
-        dweight, dposes, dw_in_smem);
+        dweight, dposes, dw_in_smem, rot_grads);
     count_launches(1);
     return check_launch(BWD ? "spnb_convsdf_backward" : "spnb_convsdf_forward") ? 1 : 0;
 }
@@ -415,12 +466,43 @@ int spnb_convsdf_forward(const float* locs, int B, int N, int D, const float* id
     return launch_convsdf<DD, false>(locs, B, N, idxs, poses, scales, S, pose_len, sdfs, sdfs_len, \
                                      sdf_offsets, sdf_shapes, nsdfs, weight, bias, O, ncells,      \
                                      kernel_size, dilation, max_distance, out, nullptr, nullptr,   \
-                                     nullptr, nullptr, stream)
+                                     nullptr, nullptr, 0, stream)
     if (D == 1) GO(1);
     if (D == 2) GO(2);
     GO(3);
 #undef GO
 }
+
+static int convsdf_backward_impl(const char* fn, int rot_grads, const float* locs, int B, int N, int D, const float* idxs,
+                          const float* poses, const float* scales, int S, int pose_len,
+                          const float* sdfs, size_t sdfs_len, const float* sdf_offsets,
+                          const float* sdf_shapes, int nsdfs, const float* weight, int O, int ncells,
+                          const float* kernel_size, const float* dilation, float max_distance,
+                          const float* grad_out, float* dlocs, float* dweight, float* dposes,
+                          void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!validate_sdf(fn, B, N, D, S, pose_len, O, ncells, nsdfs, sdfs_len)) return 0;
+    if (!locs || !idxs || !poses || !scales || !sdfs || !sdf_offsets || !sdf_shapes || !weight ||
+        !kernel_size || !dilation || !grad_out) {
+        set_error("%s: null pointer", fn);
+        return 0;
+    }
+#define GO(DD)                                                                                     \
+    return launch_convsdf<DD, true>(locs, B, N, idxs, poses, scales, S, pose_len, sdfs, sdfs_len,  \
+                                    sdf_offsets, sdf_shapes, nsdfs, weight, nullptr, O, ncells,    \
+                                    kernel_size, dilation, max_distance, nullptr, grad_out, dlocs, \
+                                    dweight, dposes, rot_grads, stream)
+    if (D == 1) GO(1);
+    if (D == 2) GO(2);
+    GO(3);
+#undef GO
+}
+
+#define SDF_BWD_ARGS                                                                              \
+    locs, B, N, D, idxs, poses, scales, S, pose_len, sdfs, sdfs_len, sdf_offsets, sdf_shapes,     \
+        nsdfs, weight, O, ncells, kernel_size, dilation, max_distance, grad_out, dlocs, dweight,  \
+        dposes, stream_
 
 int spnb_convsdf_backward(const float* locs, int B, int N, int D, const float* idxs,
                           const float* poses, const float* scales, int S, int pose_len,
@@ -430,22 +512,19 @@ int spnb_convsdf_backward(const float* locs, int B, int N, int D, const float* i
                           const float* grad_out, float* dlocs, float* dweight, float* dposes,
                           void* stream_)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (!validate_sdf("spnb_convsdf_backward", B, N, D, S, pose_len, O, ncells, nsdfs, sdfs_len)) return 0;
-    if (!locs || !idxs || !poses || !scales || !sdfs || !sdf_offsets || !sdf_shapes || !weight ||
-        !kernel_size || !dilation || !grad_out) {
-        set_error("spnb_convsdf_backward: null pointer");
-        return 0;
-    }
-#define GO(DD)                                                                                     \
-    return launch_convsdf<DD, true>(locs, B, N, idxs, poses, scales, S, pose_len, sdfs, sdfs_len,  \
-                                    sdf_offsets, sdf_shapes, nsdfs, weight, nullptr, O, ncells,    \
-                                    kernel_size, dilation, max_distance, nullptr, grad_out, dlocs, \
-                                    dweight, dposes, stream)
-    if (D == 1) GO(1);
-    if (D == 2) GO(2);
-    GO(3);
-#undef GO
+    return convsdf_backward_impl("spnb_convsdf_backward", 0, SDF_BWD_ARGS);
 }
+
+int spnb_convsdf_backward_analytic(const float* locs, int B, int N, int D, const float* idxs,
+                                   const float* poses, const float* scales, int S, int pose_len,
+                                   const float* sdfs, size_t sdfs_len, const float* sdf_offsets,
+                                   const float* sdf_shapes, int nsdfs, const float* weight, int O,
+                                   int ncells, const float* kernel_size, const float* dilation,
+                                   float max_distance, const float* grad_out, float* dlocs,
+                                   float* dweight, float* dposes, void* stream_)
+{
+    return convsdf_backward_impl("spnb_convsdf_backward_analytic", 1, SDF_BWD_ARGS);
+}
+#undef SDF_BWD_ARGS
 
 }  // extern "C"

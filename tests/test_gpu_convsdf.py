@@ -115,6 +115,61 @@ def test_convsdf_module_and_pose_finite_differences(spn, oracle):
             np.testing.assert_allclose(got_p[:, m, i], want, rtol=1e-3, atol=2e-2)
 
 
+@pytest.mark.parametrize("D,ks", [(3, (3, 1, 3)), (3, (1, 1, 1)), (2, (3, 3))])
+def test_analytic_rotation_pose_grads(spn, D, ks):
+    """compute_pose_grads="analytic": rotation columns of poses.grad from the backward kernel
+    against the float64 evaluation of the same forward formula -- both its autograd derivative and
+    central finite differences (eps 1e-6), which float32 forward differences cannot resolve.
+    The finite-difference recipe of the reference (convsdf.py:211-224) stays the default."""
+    from sdf_float64 import convsdf_float64
+    md = 0.5
+    c = cases.convsdf_case(7, B=2, N=400, D=D, S=3, O=2, ksize=ks)
+    dil = np.full(D, 0.02, np.float32)
+    sdfs, sizes = [], []
+    for i in range(c["shapes"].shape[0]):
+        shp = c["shapes"][i, :D].astype(int)
+        off = int(c["offs"][i])
+        sdfs.append(torch.from_numpy(c["sdfs"][off:off + int(np.prod(shp))].reshape(*shp).copy()))
+        sizes.append(float(c["shapes"][i, D]))
+    layer = spn.ConvSDF(sdfs, sizes, 2, D, list(ks), 0.02, md, compute_pose_grads="analytic").cuda()
+    layer.weight.data.copy_(gu.dev(c["weight"]))
+    layer.bias.data.copy_(gu.dev(c["bias"]))
+    lt = gu.dev(c["locs"]).requires_grad_(True)
+    pt = gu.dev(c["poses"]).requires_grad_(True)
+    out = layer(lt, gu.dev(c["idxs"]), pt, gu.dev(c["scales"]))
+    go = torch.rand_like(out)
+    launches = nat.lib().spnb_launch_count()
+    out.backward(go)
+    assert nat.lib().spnb_launch_count() - launches == 1, "analytic pose gradients need no extra forward passes"
+    got = gu.host(pt.grad)
+
+    def f64(poses):
+        return convsdf_float64(c["locs"], c["idxs"], poses, c["scales"], c["sdfs"], c["offs"],
+                               c["shapes"], c["weight"], c["bias"], c["ksize"], dil, md)
+    p64 = torch.from_numpy(c["poses"].astype(np.float64)).requires_grad_(True)
+    ref = f64(p64)
+    gu.assert_close(gu.host(out), ref.detach().numpy(), 1e-5, 1e-5, "fwd vs float64")
+    go64 = go.detach().cpu().double()
+    (ref * go64).sum().backward()
+    want = p64.grad.numpy()
+    scale = float(np.abs(want).max())
+    assert scale > 0.1, "degenerate case"
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=2e-5 * scale)
+    # central differences in float64 on a few rotation components
+    eps = 1e-6
+    with torch.no_grad():
+        for b, m, i in [(0, 0, D), (1, 1, c["poses"].shape[2] - 1), (0, 2, D)]:
+            if c["idxs"][b, m] < 0:
+                continue
+            hi = p64.detach().clone()
+            lo = p64.detach().clone()
+            hi[b, m, i] += eps
+            lo[b, m, i] -= eps
+            fd = float((((f64(hi) - f64(lo)) / (2 * eps)) * go64).sum())
+            assert abs(fd - want[b, m, i]) <= 1e-5 * scale + 1e-5 * abs(fd), (b, m, i, fd, want[b, m, i])
+            assert abs(fd - got[b, m, i]) <= 2e-5 * scale + 1e-4 * abs(fd), (b, m, i, fd, got[b, m, i])
+
+
 def test_2d_loc_grads(spn):
     """tests/test_convsdf.py:207-229: 2-D 2x2 SDF on a 49x49 lattice, analytic d/dlocs against
     central differences of the layer itself (eps 1e-3, atol 1e-3)."""
