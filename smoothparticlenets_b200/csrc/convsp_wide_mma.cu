@@ -44,7 +44,6 @@ constexpr int kMQ = 128;            // queries per GEMM CTA = UMMA M
 constexpr int kTQ = 8;              // queries per gather CTA (one warp each) = one 8-row group of a tile
 constexpr int kGThreads = kTQ * 32;
 constexpr int kGemmThreads = 5 * 32;  // warp 0: TMA + MMA issue; warps 1-4: accumulator flush + epilogue
-constexpr int kMaxGBytes = 104 * 1024;  // G slab per gather CTA: two CTAs per SM
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(unsigned* smem_dst, unsigned ncols)
@@ -141,24 +140,74 @@ k_wide_prep_weights(const float* __restrict__ w, float* __restrict__ img, int O,
 
 // ---- gather: G tiles as A operand images --------------------------------------------------------------------
 // gimg[tile][cell][part][ki][mi][8][4] floats: tile = 128 consecutive queries of the chunk, mi = 8-row group,
-// element (row = 8 mi + r, channel = 4 ki + e).  One CTA = 8 queries = one mi of one tile.
+// element (row = 8 mi + r, channel = 4 ki + e).  One CTA = 8 queries = one mi of one tile, one warp per query.
+//
+// A warp first compacts its query's neighbour list: the entries that survive the reference's cull test
+// (common_funcs.h:497-505) go to shared memory as (x, y, z, index), in list order.  The kernel cells are then
+// handled 32 at a time, ONE CELL PER LANE with the query's G row of that cell -- all C channels -- in the lane's
+// registers: per surviving neighbour the lane evaluates its cell's in-radius predicate and kernel weight, and the
+// neighbour's feature row (the same address for all lanes: a broadcast load) is multiplied in with C predicated
+// FMAs.  No shared-memory read-modify-write, no shuffles; the sums run in list order like the reference's.
+constexpr int kGStage = 128;  // neighbours staged per round (lists longer than this are staged once per cell pass)
+
 template <int D, int C>
-__global__ void __launch_bounds__(kGThreads)
+struct GatherLayout {
+    static constexpr int CS = C + 4;        // floats per (query, cell): lanes 16 bytes apart mod 128 -> float4 stores
+    static constexpr int QS = 32 * CS + 4;  // floats per query: = 4 (mod 32), the transposed read is conflict-free
+    static constexpr size_t bytes = sizeof(float) * ((size_t)kTQ * QS + (size_t)kTQ * kGStage * 4);
+};
+
+// One round of the list: entries [j0, j0 + kGStage) -> survivors in s_nb (list order).  Returns the number of
+// survivors; `ended` is set when the list's terminator was seen.
+template <int D>
+__device__ __forceinline__ int gather_stage(const float* __restrict__ row, int K, int j0, const float* __restrict__ sl,
+                                            const float* x, float cull2, float4* s_nb, int lane, bool& ended)
+{
+    int n = 0;
+    for (int r0 = j0; r0 < K && r0 < j0 + kGStage && !ended; r0 += 32) {
+        const int jj = r0 + lane;
+        const float nb = jj < K ? row[jj] : -1.0f;
+        const unsigned neg = __ballot_sync(0xffffffffu, !(nb >= 0.0f));
+        const unsigned before = neg ? ((1u << (__ffs(neg) - 1)) - 1u) : 0xffffffffu;  // entries ahead of the terminator
+        if (neg) ended = true;
+        bool keep = (before >> lane) & 1u;
+        float4 rec = make_float4(0.0f, 0.0f, 0.0f, nb);
+        if (keep) {
+            const float* y = sl + (size_t)(int)nb * D;
+            float d0 = 0.0f;
+            float yy[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                yy[k] = y[k];
+                d0 += (x[k] - yy[k]) * (x[k] - yy[k]);
+            }
+            rec.x = yy[0]; rec.y = yy[1]; rec.z = yy[2];
+            keep = !(d0 > cull2);
+        }
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (keep) s_nb[n + __popc(km & lanemask_lt())] = rec;
+        n += __popc(km);
+    }
+    __syncwarp();
+    return n;
+}
+
+template <int D, int C>
+__global__ void __launch_bounds__(kGThreads, 2)
 k_wide_gather(const float* __restrict__ qlocs, const float* __restrict__ locs, const float* __restrict__ data,
-              const float* __restrict__ neighbors, int q_first, int M, int N, int K, int ncells, int slab_cells,
+              const float* __restrict__ neighbors, int q_first, int M, int N, int K, int ncells,
               float radius, const float* __restrict__ ksize, const float* __restrict__ dilation, int dis_norm,
               SphParams sp, float* __restrict__ gimg)
 {
-    extern __shared__ __align__(16) float s_G[];  // [kTQ][SKP] then [slab_cells][D] cell offsets
+    using L = GatherLayout<D, C>;
+    extern __shared__ __align__(16) float s_G[];  // [kTQ][QS] G rows of one cell pass, then the staged neighbours
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int m = q_first + blockIdx.x * kTQ + warp;  // query within the scene
     const bool active = m < M;
     const size_t q = (size_t)b * M + (active ? m : 0);
-    const int SK = slab_cells * C;
-    const int SKP = SK + 4;  // row stride = 4 (mod 32) floats: the transposed read below is conflict-free
-    float* Gq = s_G + (size_t)warp * SKP;
-    float* s_off = s_G + (size_t)kTQ * SKP;
+    float* Gq = s_G + (size_t)warp * L::QS;
+    float4* s_nb = reinterpret_cast<float4*>(s_G + (size_t)kTQ * L::QS) + (size_t)warp * kGStage;
 
     int ks[D], half[D];
     float dil[D], x[D];
@@ -182,72 +231,83 @@ k_wide_gather(const float* __restrict__ qlocs, const float* __restrict__ locs, c
     const size_t img_cell = (size_t)2 * kMQ * C;  // floats per (tile, cell): hi + lo
     float* gtile = gimg + ((size_t)b * gridDim.x / (kMQ / kTQ) + tile) * ncells * img_cell;
 
-    for (int cell0 = 0; cell0 < ncells; cell0 += slab_cells) {
-        const int ncs = min(slab_cells, ncells - cell0);
-        for (int i = lane; i < SK; i += 32) Gq[i] = 0.0f;
-        for (int cl = threadIdx.x; cl < ncs; cl += kGThreads) {
-            int rem = cell0 + cl;  // kernel cell index, dimension 0 fastest (common_funcs.h:494,575-580)
+    const bool one_round = K <= kGStage;
+    int n_staged = 0;
+    bool ended = false;
+    if (active && one_round) n_staged = gather_stage<D>(row, K, 0, sl, x, cull2, s_nb, lane, ended);
+
+    for (int cell0 = 0; cell0 < ncells; cell0 += 32) {
+        const int ncs = min(32, ncells - cell0);
+        const bool valid = lane < ncs;
+        // this lane's kernel cell: query position + cell offset, dimension 0 fastest (common_funcs.h:494,575-580)
+        float xo[D];
+        {
+            int rem = valid ? cell0 + lane : 0;
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 const int ik = rem % ks[k];
                 rem /= ks[k];
-                s_off[cl * D + k] = (ik - half[k]) * dil[k];
+                xo[k] = x[k] + (ik - half[k]) * dil[k];
             }
         }
-        __syncthreads();
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0.0f;
         if (active) {
-            for (int jj = 0; jj < K; ++jj) {
-                const float nb = row[jj];
-                if (!(nb >= 0.0f)) break;  // warp-uniform: every lane reads the same entry
-                const int j = (int)nb;
-                float y[D];
-                float d0 = 0.0f;
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    y[k] = sl[(size_t)j * D + k];
-                    d0 += (x[k] - y[k]) * (x[k] - y[k]);
+            bool fin = false;
+            for (int j0 = 0; j0 < K && !fin; j0 += kGStage) {
+                if (!one_round) {
+                    __syncwarp();
+                    if (j0 == 0) ended = false;
+                    n_staged = gather_stage<D>(row, K, j0, sl, x, cull2, s_nb, lane, ended);
                 }
-                if (d0 > cull2) continue;
-                const float* dj = sd + (size_t)j * C;
-                float djr[C / 32];
-#pragma unroll
-                for (int i = 0; i < C / 32; ++i) djr[i] = dj[lane + 32 * i];
-                for (int r0 = 0; r0 < ncs; r0 += 32) {
-                    const int cl = r0 + lane;  // cell within the slab
-                    float s = 0.0f;
-                    bool hit = false;
-                    if (cl < ncs) {
-                        float d = 0.0f;
+                fin = one_round || ended;
+                for (int i = 0; i < n_staged; ++i) {
+                    const float4 rec = s_nb[i];  // broadcast
+                    float d = 0.0f;
+                    {
+                        const float yy[3] = {rec.x, rec.y, rec.z};
 #pragma unroll
                         for (int k = 0; k < D; ++k) {
-                            const float t = x[k] + s_off[cl * D + k] - y[k];
+                            const float t = xo[k] - yy[k];
                             d += t * t;
                         }
-                        if (d < rad2) {
-                            d = sqrtf(d);
-                            float norm = 1.0f;
-                            if (dis_norm && d > 0.0f) norm /= d;
-                            s = (d > sp.H ? 0.0f : sph_eval(sp.w_expr, d, sp.H, sp.w_coef)) * norm;
-                            hit = true;
-                        }
                     }
-                    unsigned mask = __ballot_sync(0xffffffffu, hit);
-                    while (mask) {
-                        const int src = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const float sc = __shfl_sync(0xffffffffu, s, src);
-                        float* g = Gq + (size_t)(r0 + src) * C;
+                    const bool hit = valid && d < rad2;
+                    if (!__any_sync(0xffffffffu, hit)) continue;
+                    float s = 0.0f;
+                    if (hit) {
+                        d = sqrtf(d);
+                        float norm = 1.0f;
+                        if (dis_norm && d > 0.0f) norm /= d;
+                        s = (d > sp.H ? 0.0f : sph_eval(sp.w_expr, d, sp.H, sp.w_coef)) * norm;
+                    }
+                    const float4* dj = reinterpret_cast<const float4*>(sd + (size_t)(int)rec.w * C);
 #pragma unroll
-                        for (int i = 0; i < C / 32; ++i) g[lane + 32 * i] = fmaf(sc, djr[i], g[lane + 32 * i]);
+                    for (int c4 = 0; c4 < C / 4; ++c4) {
+                        const float4 v = __ldg(dj + c4);  // same address in every lane
+                        if (hit) {
+                            acc[4 * c4 + 0] = fmaf(s, v.x, acc[4 * c4 + 0]);
+                            acc[4 * c4 + 1] = fmaf(s, v.y, acc[4 * c4 + 1]);
+                            acc[4 * c4 + 2] = fmaf(s, v.z, acc[4 * c4 + 2]);
+                            acc[4 * c4 + 3] = fmaf(s, v.w, acc[4 * c4 + 3]);
+                        }
                     }
                 }
             }
         }
+        // registers -> shared G rows of this pass
+        {
+            float4* g4 = reinterpret_cast<float4*>(Gq + (size_t)lane * L::CS);
+#pragma unroll
+            for (int c4 = 0; c4 < C / 4; ++c4)
+                g4[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+        }
         __syncthreads();
-        // the slab as core matrices: (cell, ki) -> 8 queries x 4 channels = 128 contiguous bytes, hi and lo
+        // the pass as core matrices: (cell, ki) -> 8 queries x 4 channels = 128 contiguous bytes, hi and lo
         for (int t = warp; t < ncs * (C / 4); t += kTQ) {
             const int cl = t / (C / 4), ki = t % (C / 4);
-            const float v = s_G[(size_t)(lane >> 2) * SKP + cl * C + 4 * ki + (lane & 3)];
+            const float v = s_G[(size_t)(lane >> 2) * L::QS + cl * L::CS + 4 * ki + (lane & 3)];
             const float hi = to_tf32(v);
             float* dst = gtile + (size_t)(cell0 + cl) * img_cell + ((size_t)ki * (kMQ / 8) + mi) * 32 + lane;
             dst[0] = hi;
@@ -414,11 +474,7 @@ int launch_convsp_wide_mma(const float* qlocs, const float* locs, const float* d
     int launches = 1;
     // measurement knob (bench.py): time the contraction alone, on whatever the image buffer holds
     const bool gemm_only = getenv("SPNB_WIDE_GEMM_ONLY") != nullptr;
-    // gather slabs: G of 8 queries x slab cells in shared memory, two CTAs per SM
-    int slab_cells = kMaxGBytes / (kTQ * C * (int)sizeof(float));
-    if (slab_cells > ncells) slab_cells = ncells;
-    slab_cells = cdiv(ncells, cdiv(ncells, slab_cells));
-    const size_t gsmem = sizeof(float) * ((size_t)kTQ * (slab_cells * C + 4) + (size_t)slab_cells * D);
+    const size_t gsmem = C == 64 ? GatherLayout<3, 64>::bytes : GatherLayout<3, 32>::bytes;
     const size_t msmem = gemm_smem_bytes(C, Opad);
     // scenes are processed one after the other when B * tiles exceeds the chunk (the image buffer is per chunk)
     const int tiles_total = cdiv(M, kMQ);
@@ -442,7 +498,7 @@ int launch_convsp_wide_mma(const float* qlocs, const float* locs, const float* d
         }                                                                                                         \
         if (!gemm_only)                                                                                           \
             k_wide_gather<DD, CC><<<ggrid, kGThreads, gsmem, stream>>>(qlocs, locs, data, neighbors, q_first, M, N, K, \
-                                                                      ncells, slab_cells, radius, kernel_size,    \
+                                                                      ncells, radius, kernel_size,                \
                                                                       dilation, dis_norm, sp, gimg);              \
         k_wide_gemm<CC><<<mgrid, kGemmThreads, msmem, stream>>>(gimg, wimg, bias, q_first, M, O, Opad, ncells, out); \
     } while (0)
