@@ -1,0 +1,296 @@
+// Shared pieces of the wide-channel ConvSP kernels (convsp_wide_mma.cu: forward, convsp_wide_bwd.cu: backward):
+// tcgen05 / tensor-memory PTX wrappers, the shared-memory operand descriptors, and the CUDA-core gather that builds
+// the G operand images.
+#pragma once
+#include <stdlib.h>
+
+#include "list_walk.cuh"
+#include "spnb_common.cuh"
+
+namespace spnb {
+
+namespace wide {
+
+constexpr int kMQ = 128;            // queries per GEMM CTA = UMMA M
+constexpr int kTQ = 8;              // queries per gather CTA (one warp each) = one 8-row group of a tile
+constexpr int kGThreads = kTQ * 32;
+constexpr int kGemmThreads = 5 * 32;  // warp 0: TMA + MMA issue; warps 1-4: accumulator flush + epilogue
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(unsigned* smem_dst, unsigned ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, 128 x N x 8, TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc,
+                                          unsigned idesc, unsigned accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 columns of fp32 -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float* v)
+{
+    unsigned r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor of a K-major operand without swizzle (cute::UMMA::SmemDescriptor, sm_100):
+// core matrices of 8 rows x 16 bytes stored as 128 contiguous bytes; `lbo` = byte distance between the two core
+// matrices an instruction's K = 8 spans, `sbo` = byte distance between 8-row groups.
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr, unsigned lbo, unsigned sbo)
+{
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3fffu);
+    d |= (unsigned long long)((lbo >> 4) & 0x3fffu) << 16;
+    d |= (unsigned long long)((sbo >> 4) & 0x3fffu) << 32;
+    d |= 1ull << 46;  // descriptor version of sm_100
+    return d;         // base offset 0, layout type 0 = no swizzle
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A and B TF32, both K-major, M x N
+__host__ __device__ constexpr unsigned umma_idesc_tf32(int M, int N)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+__device__ __forceinline__ float to_tf32(float x)
+{
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ---- gather: G tiles as A operand images --------------------------------------------------------------------
+// gimg[tile][cell][part][ki][mi][8][4] floats: tile = 128 consecutive queries of the chunk, mi = 8-row group,
+// element (row = 8 mi + r, channel = 4 ki + e).  One CTA = 8 queries = one mi of one tile, one warp per query.
+//
+// A warp first compacts its query's neighbour list: the entries that survive the reference's cull test
+// (common_funcs.h:497-505) go to shared memory as (x, y, z, index), in list order.  The kernel cells are then
+// handled 32 at a time, ONE CELL PER LANE with the query's G row of that cell -- all C channels -- in the lane's
+// registers: per surviving neighbour the lane evaluates its cell's in-radius predicate and kernel weight, and the
+// neighbour's feature row (the same address for all lanes: a broadcast load) is multiplied in with C predicated
+// FMAs.  No shared-memory read-modify-write, no shuffles; the sums run in list order like the reference's.
+constexpr int kGStage = 128;  // neighbours staged per round (lists longer than this are staged once per cell pass)
+
+template <int D, int C>
+struct GatherLayout {
+    static constexpr int CS = C + 4;        // floats per (query, cell): lanes 16 bytes apart mod 128 -> float4 stores
+    static constexpr int QS = 32 * CS + 4;  // floats per query: = 4 (mod 32), the transposed read is conflict-free
+    static constexpr int NB = kTQ * QS;              // float offset of the staged neighbours (float4 each)
+    static constexpr int ROWS = NB + kTQ * kGStage * 4;  // float offset of the per-warp feature-row rings
+    static constexpr size_t bytes = sizeof(float) * ((size_t)ROWS + (size_t)kTQ * 2 * C);
+};
+
+// Feature row of a staged neighbour -> this warp's ring slot, C/32 floats per lane (cp.async, no registers).
+template <int C>
+__device__ __forceinline__ void row_prefetch(float* ring_slot, const float* __restrict__ sd, float nb_index, int lane,
+                                             bool issue)
+{
+    if (issue) {
+        const float* src = sd + (size_t)(int)nb_index * C + lane * (C / 32);
+        const unsigned dst = smem_u32(ring_slot + lane * (C / 32));
+        if (C == 64) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// One round of the list: entries [j0, j0 + kGStage) -> survivors in s_nb (list order).  Returns the number of
+// survivors; `ended` is set when the list's terminator was seen.
+template <int D>
+__device__ __forceinline__ int gather_stage(const float* __restrict__ row, int K, int j0, const float* __restrict__ sl,
+                                            const float* x, float cull2, float4* s_nb, int lane, bool& ended)
+{
+    int n = 0;
+    for (int r0 = j0; r0 < K && r0 < j0 + kGStage && !ended; r0 += 32) {
+        const int jj = r0 + lane;
+        const float nb = jj < K ? row[jj] : -1.0f;
+        const unsigned neg = __ballot_sync(0xffffffffu, !(nb >= 0.0f));
+        const unsigned before = neg ? ((1u << (__ffs(neg) - 1)) - 1u) : 0xffffffffu;  // entries ahead of the terminator
+        if (neg) ended = true;
+        bool keep = (before >> lane) & 1u;
+        float4 rec = make_float4(0.0f, 0.0f, 0.0f, nb);
+        if (keep) {
+            const float* y = sl + (size_t)(int)nb * D;
+            float d0 = 0.0f;
+            float yy[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                yy[k] = y[k];
+                d0 += (x[k] - yy[k]) * (x[k] - yy[k]);
+            }
+            rec.x = yy[0]; rec.y = yy[1]; rec.z = yy[2];
+            keep = !(d0 > cull2);
+        }
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        if (keep) s_nb[n + __popc(km & lanemask_lt())] = rec;
+        n += __popc(km);
+    }
+    __syncwarp();
+    return n;
+}
+
+template <int D, int C>
+__global__ void __launch_bounds__(kGThreads, 2)
+k_wide_gather(const float* __restrict__ qlocs, const float* __restrict__ locs, const float* __restrict__ data,
+              const float* __restrict__ neighbors, int q_first, int M, int N, int K, int ncells,
+              float radius, const float* __restrict__ ksize, const float* __restrict__ dilation, int dis_norm,
+              SphParams sp, float* __restrict__ gimg)
+{
+    using L = GatherLayout<D, C>;
+    extern __shared__ __align__(16) float s_G[];  // [kTQ][QS] G rows of one cell pass, then the staged neighbours
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int m = q_first + blockIdx.x * kTQ + warp;  // query within the scene
+    const bool active = m < M;
+    const size_t q = (size_t)b * M + (active ? m : 0);
+    float* Gq = s_G + (size_t)warp * L::QS;
+    float4* s_nb = reinterpret_cast<float4*>(s_G + L::NB) + (size_t)warp * kGStage;
+    float* s_row = s_G + L::ROWS + (size_t)warp * 2 * C;  // two feature rows in flight
+
+    int ks[D], half[D];
+    float dil[D], x[D];
+    float maxdil = dilation[0], maxks = ksize[0];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        ks[k] = (int)ksize[k];
+        half[k] = ((int)ksize[k]) / 2;
+        dil[k] = dilation[k];
+        if (dilation[k] > maxdil) maxdil = dilation[k];
+        if (ksize[k] > maxks) maxks = ksize[k];
+        x[k] = qlocs[q * D + k];
+    }
+    const float nr = radius + ((int)maxks / 2) * maxdil * fast_root_dim(D);
+    const float cull2 = nr * nr, rad2 = radius * radius;
+    const float* row = neighbors + q * K;
+    const float* sl = locs + (size_t)b * N * D;
+    const float* sd = data + (size_t)b * N * C;
+    // this CTA's place in the image buffer
+    const int tile = blockIdx.x / (kMQ / kTQ), mi = blockIdx.x % (kMQ / kTQ);
+    const size_t img_cell = (size_t)2 * kMQ * C;  // floats per (tile, cell): hi + lo
+    float* gtile = gimg + ((size_t)b * gridDim.x / (kMQ / kTQ) + tile) * ncells * img_cell;
+
+    const bool one_round = K <= kGStage;
+    int n_staged = 0;
+    bool ended = false;
+    if (active && one_round) n_staged = gather_stage<D>(row, K, 0, sl, x, cull2, s_nb, lane, ended);
+
+    for (int cell0 = 0; cell0 < ncells; cell0 += 32) {
+        const int ncs = min(32, ncells - cell0);
+        const bool valid = lane < ncs;
+        // this lane's kernel cell: query position + cell offset, dimension 0 fastest (common_funcs.h:494,575-580)
+        float xo[D];
+        {
+            int rem = valid ? cell0 + lane : 0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const int ik = rem % ks[k];
+                rem /= ks[k];
+                xo[k] = x[k] + (ik - half[k]) * dil[k];
+            }
+        }
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+        if (active) {
+            bool fin = false;
+            for (int j0 = 0; j0 < K && !fin; j0 += kGStage) {
+                if (!one_round) {
+                    __syncwarp();
+                    if (j0 == 0) ended = false;
+                    n_staged = gather_stage<D>(row, K, j0, sl, x, cull2, s_nb, lane, ended);
+                }
+                fin = one_round || ended;
+                if (n_staged > 0) row_prefetch<C>(s_row, sd, s_nb[0].w, lane, true);
+                for (int i = 0; i < n_staged; ++i) {
+                    const float4 rec = s_nb[i];  // broadcast
+                    float d = 0.0f;
+                    {
+                        const float yy[3] = {rec.x, rec.y, rec.z};
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            const float t = xo[k] - yy[k];
+                            d += t * t;
+                        }
+                    }
+                    const bool hit = valid && d < rad2;
+                    const bool any = __any_sync(0xffffffffu, hit);  // also: every lane is done with row i-1
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");  // my part of row i has landed
+                    row_prefetch<C>(s_row + ((i + 1) & 1) * C, sd, i + 1 < n_staged ? s_nb[i + 1].w : 0.0f, lane,
+                                    i + 1 < n_staged);
+                    if (!any) continue;
+                    float s = 0.0f;
+                    if (hit) {
+                        d = sqrtf(d);
+                        float norm = 1.0f;
+                        if (dis_norm && d > 0.0f) norm /= d;
+                        s = (d > sp.H ? 0.0f : sph_eval(sp.w_expr, d, sp.H, sp.w_coef)) * norm;
+                    }
+                    __syncwarp();  // ... and everybody else's
+                    const float4* dj = reinterpret_cast<const float4*>(s_row + (i & 1) * C);
+#pragma unroll
+                    for (int c4 = 0; c4 < C / 4; ++c4) {
+                        const float4 v = dj[c4];  // same address in every lane: one broadcast wavefront
+                        if (hit) {
+                            acc[4 * c4 + 0] = fmaf(s, v.x, acc[4 * c4 + 0]);
+                            acc[4 * c4 + 1] = fmaf(s, v.y, acc[4 * c4 + 1]);
+                            acc[4 * c4 + 2] = fmaf(s, v.z, acc[4 * c4 + 2]);
+                            acc[4 * c4 + 3] = fmaf(s, v.w, acc[4 * c4 + 3]);
+                        }
+                    }
+                }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+            }
+        }
+        // registers -> shared G rows of this pass
+        {
+            float4* g4 = reinterpret_cast<float4*>(Gq + (size_t)lane * L::CS);
+#pragma unroll
+            for (int c4 = 0; c4 < C / 4; ++c4)
+                g4[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+        }
+        __syncthreads();
+        // the pass as core matrices: (cell, ki) -> 8 queries x 4 channels = 128 contiguous bytes, hi and lo
+        for (int t = warp; t < ncs * (C / 4); t += kTQ) {
+            const int cl = t / (C / 4), ki = t % (C / 4);
+            const float v = s_G[(size_t)(lane >> 2) * L::QS + cl * L::CS + 4 * ki + (lane & 3)];
+            const float hi = to_tf32(v);
+            float* dst = gtile + (size_t)(cell0 + cl) * img_cell + ((size_t)ki * (kMQ / 8) + mi) * 32 + lane;
+            dst[0] = hi;
+            dst[(size_t)kMQ * C] = to_tf32(v - hi);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace wide
+}  // namespace spnb
