@@ -148,6 +148,20 @@ int spnb_convsp_backward(const float* qlocs, const float* locs, const float* dat
                          float* ddata, float* dweight, const int* sym_flag, void* workspace,
                          void* stream);
 
+/* Backward for wide channel counts (nchannels in {32, 64}, nkernels <= 64, ndims <= 3; BASELINE.json config 3):
+ * same gradients as spnb_convsp_backward, computed in the factored form
+ *   dG[q,cell,c] = sum_o go[q,o]*weight[o,c,cell]        dweight[o,c,cell] = sum_q go[q,o]*G[q,cell,c]
+ * (two tensor-core contractions) plus one walk over the neighbour lists for ddata / dlocs / dqlocs.  Any of the
+ * four outputs may be NULL; dqlocs == dlocs (one buffer for both roles) requires M == N.  `workspace`:
+ * spnb_convsp_backward_wide_workspace_bytes() bytes (0 = shape not supported: use spnb_convsp_backward). */
+size_t spnb_convsp_backward_wide_workspace_bytes(int nkernels, int nchannels, int ndims, int ncells);
+int spnb_convsp_backward_wide(const float* qlocs, const float* locs, const float* data,
+                              const float* neighbors, const float* weight, int batch_size, int M, int N,
+                              int nchannels, int ndims, int max_neighbors, int nkernels, int ncells,
+                              float radius, const float* kernel_size, const float* dilation, int dis_norm,
+                              int kernel_fn, const float* grad_out, float* dqlocs, float* dlocs, float* ddata,
+                              float* dweight, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- fused ConvSP group (no reference counterpart) ------------------------ */
 
 /* Several ConvSP layers with kernel_size 1 that share (locs, neighbors, radius) and use the particles

@@ -165,8 +165,20 @@ class _ConvSPFunction(torch.autograd.Function):
             dd = torch.empty(B, N, C, device=dev, dtype=torch.float32)
         if need_w:
             dw = torch.empty_like(weight)
-        if dq is not None or dl is not None or dd is not None or dw is not None:
-            L = nat.lib()
+        L = nat.lib()
+        wide_bytes = (L.spnb_convsp_backward_wide_workspace_bytes(O, C, D, ncells)
+                      if C * O * ncells >= 4096 else 0)
+        if wide_bytes and (dq is not None or dl is not None or dd is not None or dw is not None):
+            # wide channel counts: two tensor-core contractions + one list walk (csrc/convsp_wide_bwd.cu)
+            ws = torch.empty((wide_bytes + 3) // 4, device=dev, dtype=torch.float32)
+            with torch.cuda.device(dev):
+                nat.check(L.spnb_convsp_backward_wide(
+                    nat.ptr(q), nat.ptr(locs), nat.ptr(data), nat.ptr(neighbors), nat.ptr(weight),
+                    B, M, N, C, D, K, O, ncells, radius, nat.ptr(kernel_size), nat.ptr(dilation),
+                    dis_norm, kernel_fn, nat.ptr(grad_output), nat.ptr(dq), nat.ptr(dl),
+                    nat.ptr(dd), nat.ptr(dw), nat.ptr(ws), wide_bytes, nat.stream()),
+                    "spnb_convsp_backward_wide")
+        elif dq is not None or dl is not None or dd is not None or dw is not None:
             with torch.cuda.device(dev):
                 nat.check(L.spnb_convsp_backward(
                     nat.ptr(q), nat.ptr(locs), nat.ptr(data), nat.ptr(neighbors), nat.ptr(weight),

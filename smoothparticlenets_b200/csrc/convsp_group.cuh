@@ -177,34 +177,7 @@ struct GroupArgs {
     float H, invH, H2, rad2;
 };
 
-struct SphF { float H, invH, H2; };
-
-__device__ __forceinline__ float sph_fast(int e, float d, float d2, float c, const SphF& p)
-{
-    switch (e) {
-    case E_DEFAULT:   { const float q = p.H2 - d2; return c * q * q * q; }
-    case E_DDEFAULT:  { const float q = p.H2 - d2; return c * q * q * d; }
-    case E_DDEFAULT2: return c * (p.H2 * p.H2 + d2 * (5.0f * d2 - 6.0f * p.H2));
-    case E_D_DDEFAULT2: return c * d * (20.0f * d2 - 12.0f * p.H2);
-    case E_PRESSURE:  { const float q = p.H - d; return c * q * q * q; }
-    case E_DPRESSURE: { const float q = p.H - d; return c * q * q; }
-    case E_DPRESSURE2: return c * (p.H - d);
-    case E_D_DPRESSURE2: return c;
-    case E_INDIRECT:  return p.H - d;
-    case E_D_INDIRECT: return -1.0f;
-    case E_CONSTANT:  return 1.0f;
-    case E_D_CONSTANT: return 0.0f;
-    case E_SPIKY:     { const float q = fmaf(-d, p.invH, 1.0f); return c * q * q; }
-    case E_DSPIKY:    return c * fmaf(-d, p.invH, 1.0f);
-    case E_D_DSPIKY:  return c;
-    case E_COHESION:  { const float t = d * p.invH; return fmaf(fmaf(-6.0f, t, 7.0f) * t, t, -1.0f); }
-    case E_D_COHESION: return 2.0f * d * (7.0f * p.H - 9.0f * d) * (p.invH * p.invH * p.invH);
-    case E_SIGMOID:   return 1.0f / (1.0f + expf((d - 0.2f * p.H) * 20.0f * p.invH));
-    case E_D_SIGMOID: { const float ex = expf((d - 0.2f * p.H) * 20.0f * p.invH);
-                        return -20.0f * ex * p.invH / ((ex + 1.0f) * (ex + 1.0f)); }
-    default: return 0.0f;
-    }
-}
+// SphF / sph_fast: spnb_common.cuh
 
 // ---- pack pre-pass ----------------------------------------------------------------------------------
 // Planar (one float4 array per record quarter) for the tile kernels, record-major for the list walk; which one

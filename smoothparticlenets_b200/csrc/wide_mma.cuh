@@ -158,7 +158,10 @@ __device__ __forceinline__ int gather_stage(const float* __restrict__ row, int K
     return n;
 }
 
-template <int D, int C>
+// T == false: gimg as above.  T == true (dweight): the transposed image gimg[tile][cell group][part][kq][mi][8][4]
+// with rows (cell within the group of 128/C cells, channel) and K = the tile's queries: element
+// (row = 8 mi + r, query = 4 kq + e).
+template <int D, int C, bool T = false>
 __global__ void __launch_bounds__(kGThreads, 2)
 k_wide_gather(const float* __restrict__ qlocs, const float* __restrict__ locs, const float* __restrict__ data,
               const float* __restrict__ neighbors, int q_first, int M, int N, int K, int ncells,
@@ -193,6 +196,8 @@ k_wide_gather(const float* __restrict__ qlocs, const float* __restrict__ locs, c
     const float* row = neighbors + q * K;
     const float* sl = locs + (size_t)b * N * D;
     const float* sd = data + (size_t)b * N * C;
+    const SphF sf = {sp.H, 1.0f / sp.H, sp.H * sp.H};
+    const float wcoef = (float)(sp.w_expr == E_DSPIKY ? sp.w_coef / (double)sp.H : sp.w_coef);  // sph_fast's convention
     // this CTA's place in the image buffer
     const int tile = blockIdx.x / (kMQ / kTQ), mi = blockIdx.x % (kMQ / kTQ);
     const size_t img_cell = (size_t)2 * kMQ * C;  // floats per (tile, cell): hi + lo
@@ -249,10 +254,9 @@ k_wide_gather(const float* __restrict__ qlocs, const float* __restrict__ locs, c
                     if (!any) continue;
                     float s = 0.0f;
                     if (hit) {
-                        d = sqrtf(d);
-                        float norm = 1.0f;
-                        if (dis_norm && d > 0.0f) norm /= d;
-                        s = (d > sp.H ? 0.0f : sph_eval(sp.w_expr, d, sp.H, sp.w_coef)) * norm;
+                        const float dist = sqrtf(d);  // exact: decides the d > H guard like the reference
+                        s = dist > sp.H ? 0.0f : sph_fast(sp.w_expr, dist, d, wcoef, sf);
+                        if (dis_norm && dist > 0.0f) s *= fast_rsqrt(d);
                     }
                     __syncwarp();  // ... and everybody else's
                     const float4* dj = reinterpret_cast<const float4*>(s_row + (i & 1) * C);
@@ -279,14 +283,34 @@ k_wide_gather(const float* __restrict__ qlocs, const float* __restrict__ locs, c
                 g4[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
         }
         __syncthreads();
-        // the pass as core matrices: (cell, ki) -> 8 queries x 4 channels = 128 contiguous bytes, hi and lo
-        for (int t = warp; t < ncs * (C / 4); t += kTQ) {
-            const int cl = t / (C / 4), ki = t % (C / 4);
-            const float v = s_G[(size_t)(lane >> 2) * L::QS + cl * L::CS + 4 * ki + (lane & 3)];
-            const float hi = to_tf32(v);
-            float* dst = gtile + (size_t)(cell0 + cl) * img_cell + ((size_t)ki * (kMQ / 8) + mi) * 32 + lane;
-            dst[0] = hi;
-            dst[(size_t)kMQ * C] = to_tf32(v - hi);
+        if (!T) {
+            // the pass as core matrices: (cell, ki) -> 8 queries x 4 channels = 128 contiguous bytes, hi and lo;
+            // a lane moves one query's 4 channels, a quarter warp one core matrix
+            const int qq = lane & 7, kk = lane >> 3;
+            for (int t = warp; t < ncs * (C / 16); t += kTQ) {
+                const int cl = t / (C / 16), ki = 4 * (t % (C / 16)) + kk;
+                const float4 v = *reinterpret_cast<const float4*>(s_G + (size_t)qq * L::QS + cl * L::CS + 4 * ki);
+                float4 hi, lo;
+                hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
+                lo.x = to_tf32(v.x - hi.x); lo.y = to_tf32(v.y - hi.y); lo.z = to_tf32(v.z - hi.z); lo.w = to_tf32(v.w - hi.w);
+                float* dst = gtile + (size_t)(cell0 + cl) * img_cell + ((size_t)ki * (kMQ / 8) + mi) * 32 + qq * 4;
+                *reinterpret_cast<float4*>(dst) = hi;
+                *reinterpret_cast<float4*>(dst + (size_t)kMQ * C) = lo;
+            }
+        } else {
+            constexpr int CPG = kMQ / C;
+            const int ncg = (ncells + CPG - 1) / CPG;
+            float* ttile = gimg + ((size_t)b * gridDim.x / (kMQ / kTQ) + tile) * ncg * ((size_t)2 * kMQ * kMQ);
+            // core matrix (cell, ci, query half): 8 channels x 4 queries
+            for (int t = warp; t < ncs * (C / 8) * 2; t += kTQ) {
+                const int qh = t & 1, ci = (t >> 1) % (C / 8), cl = (t >> 1) / (C / 8);
+                const float v = s_G[(size_t)(4 * qh + (lane & 3)) * L::QS + cl * L::CS + 8 * ci + (lane >> 2)];
+                const float hi = to_tf32(v);
+                const int cell = cell0 + cl, cg = cell / CPG, rowgrp = (cell % CPG) * (C / 8) + ci, kq = 2 * mi + qh;
+                float* dst = ttile + (size_t)cg * ((size_t)2 * kMQ * kMQ) + ((size_t)kq * (kMQ / 8) + rowgrp) * 32 + lane;
+                dst[0] = hi;
+                dst[(size_t)kMQ * kMQ] = to_tf32(v - hi);
+            }
         }
         __syncthreads();
     }

@@ -281,6 +281,69 @@ def test_wide_channel_forward(spn, oracle, D, ks, C, O, fn, dn):
         gu.assert_close(gu.host(out), want, RTOL, 1e-6 * max(1.0, float(np.abs(terms).max())), "module fwd")
 
 
+@pytest.mark.parametrize("D,ks,C,O,fn,dn,alias,K", [(3, (3, 3, 3), 64, 64, "spiky", 0, False, 64),
+                                                    (3, (3, 3, 3), 64, 40, "default", 1, True, 64),
+                                                    (2, (5, 5), 32, 64, "cohesion", 0, False, 160),
+                                                    (3, (5, 1, 3), 32, 16, "dspiky", 1, True, 48)])
+def test_wide_channel_backward(spn, oracle, D, ks, C, O, fn, dn, alias, K):
+    """All four gradients of the wide-channel shapes through the tensor-core backward (csrc/convsp_wide_bwd.cu:
+    dG and dweight as tcgen05 3xTF32 contractions, one list walk for ddata / dlocs / dqlocs) against the oracle;
+    both sides are measured against a float64 evaluation because every entry sums 10^4..10^6 signed terms.
+    alias: qlocs is None, i.e. one gradient buffer receives d/dqlocs + d/dlocs.  K = 160: lists longer than the
+    128-entry staging round."""
+    from test_gpu_parity_configs import closer_than_reference, convsp_float64
+    from smoothparticlenets_b200 import _native as nat
+    B, N = 2, 300
+    M = N if alias else 45
+    r = cases.rng(21)
+    R = {2: 0.09, 3: 0.2}[D]
+    if K > 128:
+        R = 0.25  # long lists
+    dil = 0.4 * R
+    locs = r.rand(B, N, D).astype(np.float32)
+    qlocs = locs if alias else r.rand(B, M, D).astype(np.float32)
+    data = r.randn(B, N, C).astype(np.float32)
+    weight = (r.randn(O, C, int(np.prod(ks))) / np.sqrt(C * np.prod(ks))).astype(np.float32)
+    bias = r.rand(O).astype(np.float32)
+    nl, nd, q, nb = build_lists(oracle, locs, data, qlocs, R + dil * max((k - 1) / 2 for k in ks), K=K)
+    if alias:
+        q = nl  # the particles, in their sorted order, are their own queries
+    if K > 128:
+        assert (nb >= 0).sum(-1).max() > 128
+    ks_np, dil_np = np.array(ks, np.float32), np.full(D, dil, np.float32)
+    go = r.randn(B, M, O).astype(np.float32)
+    assert nat.lib().spnb_convsp_backward_wide_workspace_bytes(O, C, D, int(np.prod(ks))) > 0
+    conv = spn.ConvSP(C, O, D, ks, dil, R, dis_norm=bool(dn), kernel_fn=fn).cuda()
+    conv.weight.data.copy_(gu.dev(weight))
+    conv.bias.data.copy_(gu.dev(bias))
+    lt = gu.dev(nl).requires_grad_(True)
+    dt = gu.dev(nd).requires_grad_(True)
+    qt = None if alias else gu.dev(q).requires_grad_(True)
+    out = conv(lt, dt, gu.dev(nb), qt)
+    n0 = nat.lib().spnb_launch_count()
+    out.backward(gu.dev(go))
+    # transposed weights, go images, dG GEMM, list walk, transposed gather, dweight GEMM
+    assert nat.lib().spnb_launch_count() - n0 == 6
+    wq, wl, wd, ww, wb = oracle.convsp_backward(q, nl, nd, nb, weight, bias, R, ks_np, dil_np, dn, fn, go)
+    _, w64, q64, l64, d64 = convsp_float64(spn, q, nl, nd, nb, weight, bias, go, R, ks, [dil] * D, dn, fn, grads=True)
+    if alias:
+        closer_than_reference(gu.host(lt.grad), wq + wl, q64 + l64, "wide dlocs (+dqlocs)")
+    else:
+        closer_than_reference(gu.host(qt.grad), wq, q64, "wide dqlocs")
+        closer_than_reference(gu.host(lt.grad), wl, l64, "wide dlocs")
+    closer_than_reference(gu.host(dt.grad), wd, d64, "wide ddata")
+    closer_than_reference(gu.host(conv.weight.grad), ww, w64, "wide dweight")
+    gu.assert_close(gu.host(conv.bias.grad), wb, 1e-5, 1e-5 * float(np.abs(wb).max()), "wide dbias")
+    # only some gradients requested
+    dt2 = gu.dev(nd).requires_grad_(True)
+    for p_ in conv.parameters():
+        p_.requires_grad_(False)
+    out2 = conv(gu.dev(nl), dt2, gu.dev(nb), None if alias else gu.dev(q))
+    out2.backward(gu.dev(go))
+    # (float atomics: the order of the additions differs from run to run)
+    assert float((dt2.grad - dt.grad).abs().max()) <= 1e-5 * float(dt.grad.abs().max())
+
+
 def test_full_size_properties(spn):
     """BASELINE.json config 2 size (8 x 65536 particles): size-independent properties of ConvSP --
     the `constant` kernel with unit data counts neighbours, outputs are linear in the data, the fused
