@@ -35,7 +35,7 @@ def _time_steps(torch, fn, steps, warmup, barrier):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# c3: ConvSP wide-channel forward (+ backward through the generic kernels), 64 -> 64, kernel_size 5
+# c3: ConvSP wide-channel forward and backward (tcgen05 contractions), 64 -> 64, kernel_size 5
 # ------------------------------------------------------------------------------------------------------------
 def run_c3(args, ClockSampler):
     import torch
@@ -78,6 +78,28 @@ def run_c3(args, ClockSampler):
     os.environ["SPNB_WIDE_GEMM_ONLY"] = "1"
     ms_gemm = _time_steps(torch, fwd, args.steps, 1, torch.cuda.synchronize) / args.steps
     del os.environ["SPNB_WIDE_GEMM_ONLY"]
+    # backward (all four gradients) on the same queries: dG / dweight contractions + list walk + transposed gather
+    conv_g = spn.ConvSP(C, O, D, KS, DIL, R, kernel_fn="spiky").cuda()
+    with torch.no_grad():
+        conv_g.weight.copy_(conv.weight)
+        conv_g.bias.copy_(conv.bias)
+    slg, sdg, qg = (t.detach().clone().requires_grad_(True) for t in (sl, sd, q))
+    go = torch.rand(out.shape, device="cuda", generator=g)
+    bwd_state = {}
+
+    def fwd_g():
+        bwd_state["out"] = conv_g(slg, sdg, nb, qg)
+
+    def fwd_bwd():
+        fwd_g()
+        for t in (slg, sdg, qg, conv_g.weight, conv_g.bias):
+            t.grad = None
+        bwd_state["out"].backward(go)
+    bsteps = max(2, args.steps // 2)
+    ms_fwd_g = _time_steps(torch, fwd_g, bsteps, 2, torch.cuda.synchronize) / bsteps
+    ms_fb = _time_steps(torch, fwd_bwd, bsteps, 2, torch.cuda.synchronize) / bsteps
+    ms_bwd = ms_fb - ms_fwd_g
+    del bwd_state["out"]
     # e2e: host positions / features / lists in, output out, every step
     hq, hl, hd, hn = (t.cpu().pin_memory() for t in (q, sl, sd, nb))
     ho = torch.empty(out.shape).pin_memory()
@@ -105,6 +127,11 @@ def run_c3(args, ClockSampler):
         "e2e": {"value": M / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": sum(t.numel() * 4 for t in (hq, hl, hd, hn)), "d2h_bytes_per_step": ho.numel() * 4},
         "gpu_launches": int(launches),
+        "backward": {"ms_per_step": ms_bwd, "queries_per_s": M / (ms_bwd * 1e-3), "vs_forward": ms_bwd / t_ms,
+                     "gradients": "dqlocs, dlocs, ddata, dweight, dbias",
+                     "contraction_tflops": 2.0 * flops / (ms_bwd * 1e-3) / 1e12,
+                     "note": "backward time = (forward + backward) - forward, CUDA events; the two contractions "
+                             "(dG = go*W, dweight = go^T*G) are 2x the forward's dense FLOPs"},
         # the contraction (k_wide_gemm + weight images): 3 TF32 MMAs per product; it streams the A operand images
         # (2 x 32 KB per 128 queries and kernel cell) from HBM, which is what bounds it
         "roofline": {"bound": "tensor", "kernel": "k_wide_gemm", "achieved": flops / (ms_gemm * 1e-3) / 1e12,

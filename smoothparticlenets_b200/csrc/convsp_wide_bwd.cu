@@ -229,6 +229,7 @@ k_wide_scatter(const float* __restrict__ qlocs, const float* __restrict__ locs, 
     float* Gq = s_G + (size_t)warp * L::QS;
     float4* s_nb = reinterpret_cast<float4*>(s_G + L::NB) + (size_t)warp * kGStage;
     float* s_row = s_G + L::ROWS + (size_t)warp * 2 * C;
+    float* s_sw = s_G + L::SW + (size_t)warp * 32;
 
     int ks[D], half[D];
     float dil[D], x[D];
@@ -360,21 +361,30 @@ k_wide_scatter(const float* __restrict__ qlocs, const float* __restrict__ locs, 
                     }
                 }
                 if (ddb) {
-                    // lanes as channels: sum over the hit cells of S * dG[cell][c]
-                    float a[C / 32];
+                    // lanes as channels (C = 64: the pair 2 lane, 2 lane + 1): sum over the cells of S * dG[cell][c];
+                    // the cell weights go through shared memory, four per broadcast load
+                    s_sw[lane] = s;  // 0 where the cell is not hit
+                    __syncwarp();
+                    float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-                    for (int u = 0; u < C / 32; ++u) a[u] = 0.0f;
-                    unsigned mask = hits;
-                    while (mask) {
-                        const int src = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const float sc = __shfl_sync(0xffffffffu, s, src);
-                        const float* g = Gq + (size_t)src * L::CS;
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        if (!((hits >> (4 * c4)) & 0xFu)) continue;
+                        const float4 s4 = *reinterpret_cast<const float4*>(s_sw + 4 * c4);
+                        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-                        for (int u = 0; u < C / 32; ++u) a[u] = fmaf(sc, g[lane + 32 * u], a[u]);
+                        for (int e = 0; e < 4; ++e) {
+                            const float* g = Gq + (size_t)(4 * c4 + e) * L::CS;
+                            if (C == 64) {
+                                const float2 v = *reinterpret_cast<const float2*>(g + 2 * lane);
+                                a0 = fmaf(sv[e], v.x, a0);
+                                a1 = fmaf(sv[e], v.y, a1);
+                            } else {
+                                a0 = fmaf(sv[e], g[lane], a0);
+                            }
+                        }
                     }
-#pragma unroll
-                    for (int u = 0; u < C / 32; ++u) atomicAdd(ddb + (size_t)j * C + lane + 32 * u, a[u]);
+                    if (C == 64) atomicAdd(reinterpret_cast<float2*>(ddb + (size_t)j * C) + lane, make_float2(a0, a1));
+                    else atomicAdd(ddb + (size_t)j * C + lane, a0);
                 }
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -106,7 +106,8 @@ struct GatherLayout {
     static constexpr int QS = 32 * CS + 4;  // floats per query: = 4 (mod 32), the transposed read is conflict-free
     static constexpr int NB = kTQ * QS;              // float offset of the staged neighbours (float4 each)
     static constexpr int ROWS = NB + kTQ * kGStage * 4;  // float offset of the per-warp feature-row rings
-    static constexpr size_t bytes = sizeof(float) * ((size_t)ROWS + (size_t)kTQ * 2 * C);
+    static constexpr int SW = ROWS + kTQ * 2 * C;    // float offset of the per-warp cell weights (backward)
+    static constexpr size_t bytes = sizeof(float) * ((size_t)SW + (size_t)kTQ * 32);
 };
 
 // Feature row of a staged neighbour -> this warp's ring slot, C/32 floats per lane (cp.async, no registers).
