@@ -275,6 +275,34 @@ int spnb_convsdf_backward_analytic(const float* locs, int batch_size, int N, int
                                    float max_distance, const float* grad_out, float* dlocs,
                                    float* dweight, float* dposes, void* stream);
 
+/* ---- ParticleProjection / ImageProjection (3-D particles in camera space) -------------------------------- */
+
+/* Gaussian splat of every particle into out [batch_size, height, width] (zero-filled here).  Replaces
+ * cuda_particleprojection with dlocs == NULL (gpu_kernels.h:111-123; compute_particle_projection,
+ * common_funcs.h:979-1052).  depth_mask [batch_size, height, width]: a particle behind a positive mask value
+ * does not contribute to that pixel. */
+int spnb_particleprojection_forward(const float* locs, int batch_size, int N, float camera_fl, int width,
+                                    int height, float filter_std, float filter_scale, const float* depth_mask,
+                                    float* out, void* stream);
+/* dlocs [batch_size, N, 3] = d(loss)/d(locs) given grad_out = d(loss)/d(out); written, not accumulated.
+ * Replaces cuda_particleprojection with dlocs != NULL (where `out` carries grad_out). */
+int spnb_particleprojection_backward(const float* locs, int batch_size, int N, float camera_fl, int width,
+                                     int height, float filter_std, float filter_scale, const float* depth_mask,
+                                     const float* grad_out, float* dlocs, void* stream);
+
+/* Bilinear sample of image [batch_size, channels, height, width] at each particle's pixel position into out
+ * [batch_size, N, channels] (0 for particles behind the camera, outside the image or behind the depth mask).
+ * Replaces cuda_imageprojection with NULL gradients (gpu_kernels.h:125-138; compute_image_projection,
+ * common_funcs.h:1087-1183). */
+int spnb_imageprojection_forward(const float* locs, const float* image, int batch_size, int N, float camera_fl,
+                                 int width, int height, int channels, const float* depth_mask, float* out,
+                                 void* stream);
+/* dlocs [batch_size, N, 3] written, dimage [batch_size, channels, height, width] zero-filled here and
+ * accumulated; either may be NULL. */
+int spnb_imageprojection_backward(const float* locs, const float* image, int batch_size, int N, float camera_fl,
+                                  int width, int height, int channels, const float* depth_mask,
+                                  const float* grad_out, float* dlocs, float* dimage, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -663,3 +663,95 @@ void spno_convsdf(const float* locs, int B, int N, int D, const float* idxs, con
     free(live);
     free(centre_v);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * ParticleProjection / ImageProjection (3-D only).  Restates compute_particle_projection and
+ * compute_image_projection (src/common_funcs.h:979-1052 and 1087-1183) and their CPU drivers
+ * (src/cpu_layer_funcs.cpp:428-486, 489-556): particles are already in camera space.
+ * The pixel loops run on FLOAT counters exactly as the reference writes them.
+ * ---------------------------------------------------------------------------------------------- */
+/* go == NULL: forward, adds the Gaussians into out [B,H,W] (caller zero-fills).
+ * go != NULL: backward, go = dL/dout [B,H,W]; adds into dlocs [B,N,3] (caller zero-fills). */
+void spno_particleprojection(const float* locs, int B, int N, float camera_fl, int width, int height,
+                             float filter_std, float filter_scale, const float* depth_mask, float* out,
+                             const float* go, float* dlocs)
+{
+    for (int b = 0; b < B; ++b)
+        for (int n = 0; n < N; ++n) {
+            const float* rr = locs + ((size_t)b * N + n) * 3;
+            const float rx = rr[0], ry = rr[1], rz = rr[2];
+            if (rz <= 0) continue;
+            const float px = rx * camera_fl / rz + width / 2;
+            const float py = ry * camera_fl / rz + height / 2;
+            const int s = ceilf(filter_std * 2);
+            const float s2 = s * s;
+            const float f = filter_scale / (filter_std * sqrtf(2 * M_PI));
+            const float std2 = filter_std * filter_std;
+            float i, j;
+            for (i = (px - s > 0 ? px - s : 0); i < width && i < px + s + 1; i += 1)
+                for (j = (py - s > 0 ? py - s : 0); j < height && j < py + s + 1; j += 1) {
+                    const int ii = i, jj = j;
+                    const size_t pix = (size_t)b * width * height + (size_t)jj * width + ii;
+                    const float depth_val = depth_mask[pix];
+                    if (depth_val > 0.0f && depth_val < rz) continue;
+                    const float xi = ii + 0.5f, yj = jj + 0.5f;
+                    const float d2 = (xi - px) * (xi - px) + (yj - py) * (yj - py);
+                    if (d2 > s2) continue;
+                    const float v = f * expf(-d2 / (2.0f * std2));
+                    if (!go) {
+                        out[pix] += v;
+                    } else {
+                        const float g = go[pix];
+                        float* dl = dlocs + ((size_t)b * N + n) * 3;
+                        dl[0] += g * (xi - px) * v / std2 * camera_fl / rz;
+                        dl[1] += g * (yj - py) * v / std2 * camera_fl / rz;
+                        dl[2] += g * v / std2 * camera_fl / (rz * rz) * ((xi - px) * -rx + (yj - py) * -ry);
+                    }
+                }
+        }
+}
+
+/* go == NULL: forward into out [B,N,C] (caller zero-fills).  go != NULL: backward, go = dL/dout;
+ * adds into dlocs [B,N,3] and dimage [B,C,H,W] (caller zero-fills both). */
+void spno_imageprojection(const float* locs, const float* image, int B, int N, float camera_fl, int width,
+                          int height, int channels, const float* depth_mask, float* out, const float* go,
+                          float* dlocs, float* dimage)
+{
+    for (int b = 0; b < B; ++b)
+        for (int n = 0; n < N; ++n) {
+            const float* rr = locs + ((size_t)b * N + n) * 3;
+            const float rx = rr[0], ry = rr[1], rz = rr[2];
+            if (rz <= 0) continue;
+            const float px = rx * camera_fl / rz + width / 2;
+            const float py = ry * camera_fl / rz + height / 2;
+            if (px <= 0.5 || px >= width - 0.5 || py <= 0.5 || py >= height - 0.5) continue;
+            const int ii = px, jj = py;
+            const float depth_val = depth_mask[(size_t)b * width * height + (size_t)jj * width + ii];
+            if (depth_val > 0.0f && depth_val < rz) continue;
+            for (int c = 0; c < channels; ++c) {
+                const int lowi = px - 0.5, highi = px + 0.5, lowj = py - 0.5, highj = py + 0.5;
+                const float di = px - 0.5 - lowi, dj = py - 0.5 - lowj;
+                const size_t plane = ((size_t)b * channels + c) * width * height;
+                const float* ip = image + plane;
+                const float vll = ip[lowj * width + lowi], vlh = ip[highj * width + lowi];
+                const float vhl = ip[lowj * width + highi], vhh = ip[highj * width + highi];
+                const float v = vll * (1 - di) * (1 - dj) + vlh * (1 - di) * dj + vhl * di * (1 - dj) + vhh * di * dj;
+                if (!go) {
+                    out[((size_t)b * N + n) * channels + c] += v;
+                } else {
+                    const float g = go[((size_t)b * N + n) * channels + c];
+                    const float doutpx = -vll * (1 - dj) + -vlh * dj + vhl * (1 - dj) + vhh * dj;
+                    const float doutpy = -vll * (1 - di) + vlh * (1 - di) + -vhl * di + vhh * di;
+                    float* dl = dlocs + ((size_t)b * N + n) * 3;
+                    dl[0] += g * camera_fl / rz * doutpx;
+                    dl[1] += g * camera_fl / rz * doutpy;
+                    dl[2] += g * -rx * camera_fl / (rz * rz) * doutpx + g * -ry * camera_fl / (rz * rz) * doutpy;
+                    float* dp = dimage + plane;
+                    dp[lowj * width + lowi] += g * (1 - di) * (1 - dj);
+                    dp[highj * width + lowi] += g * (1 - di) * dj;
+                    dp[lowj * width + highi] += g * di * (1 - dj);
+                    dp[highj * width + highi] += g * di * dj;
+                }
+            }
+        }
+}

@@ -60,7 +60,8 @@ class COracle(object):
         L.spno_kernel_dw.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_int]
         for name in ("spno_grid_bounds", "spno_cell_keys", "spno_hashgrid_order_selection",
                      "spno_hashgrid_order_stable", "spno_reorder_data", "spno_cell_table",
-                     "spno_compute_collisions", "spno_convsp", "spno_convsdf"):
+                     "spno_compute_collisions", "spno_convsp", "spno_convsdf", "spno_particleprojection",
+                     "spno_imageprojection"):
             getattr(L, name).restype = None
 
     # ---- SPH kernels -------------------------------------------------------------------------
@@ -194,6 +195,46 @@ class COracle(object):
         return dl, dw, dp, go.sum(1).sum(0)
 
 
+    # ---- ParticleProjection / ImageProjection (camera-space particles) ------------------------------
+    def particleprojection_forward(self, locs, camera_fl, filter_std, filter_scale, depth_mask):
+        locs, dm = _f(locs), _f(depth_mask)
+        B, N, _ = locs.shape
+        H, W = dm.shape[1], dm.shape[2]
+        out = np.zeros((B, H, W), np.float32)
+        self.lib.spno_particleprojection(_p(locs), B, N, ctypes.c_float(camera_fl), W, H,
+                                         ctypes.c_float(filter_std), ctypes.c_float(filter_scale), _p(dm),
+                                         _p(out), None, None)
+        return out
+
+    def particleprojection_backward(self, locs, camera_fl, filter_std, filter_scale, depth_mask, grad_out):
+        locs, dm, go = _f(locs), _f(depth_mask), _f(grad_out)
+        B, N, _ = locs.shape
+        H, W = dm.shape[1], dm.shape[2]
+        dl = np.zeros_like(locs)
+        self.lib.spno_particleprojection(_p(locs), B, N, ctypes.c_float(camera_fl), W, H,
+                                         ctypes.c_float(filter_std), ctypes.c_float(filter_scale), _p(dm),
+                                         None, _p(go), _p(dl))
+        return dl
+
+    def imageprojection_forward(self, locs, image, camera_fl, depth_mask):
+        locs, image, dm = _f(locs), _f(image), _f(depth_mask)
+        B, N, _ = locs.shape
+        C, H, W = image.shape[1:]
+        out = np.zeros((B, N, C), np.float32)
+        self.lib.spno_imageprojection(_p(locs), _p(image), B, N, ctypes.c_float(camera_fl), W, H, C, _p(dm),
+                                      _p(out), None, None, None)
+        return out
+
+    def imageprojection_backward(self, locs, image, camera_fl, depth_mask, grad_out):
+        locs, image, dm, go = _f(locs), _f(image), _f(depth_mask), _f(grad_out)
+        B, N, _ = locs.shape
+        C, H, W = image.shape[1:]
+        dl, di = np.zeros_like(locs), np.zeros_like(image)
+        self.lib.spno_imageprojection(_p(locs), _p(image), B, N, ctypes.c_float(camera_fl), W, H, C, _p(dm),
+                                      None, _p(go), _p(dl), _p(di))
+        return dl, di
+
+
 class RefOracle(object):
     """The unmodified reference CPU extension (oracle/_ref), same methods as COracle."""
     kind = "reference"
@@ -290,6 +331,32 @@ class RefOracle(object):
             dp = t.zeros(a[2].shape[0] + 1)  # "disabled" marker, convsdf.py:192-196
         self.ext.spn_convsdf_backward(*a, float(max_distance), go, dl, dw, dp)
         return dl.numpy(), dw.numpy(), (dp.numpy() if pose_grads else None), go.sum(1).sum(0).numpy()
+
+
+    def particleprojection_forward(self, locs, camera_fl, filter_std, filter_scale, depth_mask):
+        l, dm = self._t(locs), self._t(depth_mask)
+        out = self.torch.zeros(dm.shape)
+        self.ext.spn_particleprojection_forward(l, float(camera_fl), float(filter_std), float(filter_scale), dm, out)
+        return out.numpy()
+
+    def particleprojection_backward(self, locs, camera_fl, filter_std, filter_scale, depth_mask, grad_out):
+        l, dm, go = self._t(locs), self._t(depth_mask), self._t(grad_out)
+        dl = self.torch.zeros(l.shape)
+        self.ext.spn_particleprojection_backward(l, float(camera_fl), float(filter_std), float(filter_scale), dm,
+                                                 go, dl)
+        return dl.numpy()
+
+    def imageprojection_forward(self, locs, image, camera_fl, depth_mask):
+        l, im, dm = self._t(locs), self._t(image), self._t(depth_mask)
+        out = self.torch.zeros(l.shape[0], l.shape[1], im.shape[1])
+        self.ext.spn_imageprojection_forward(l, im, float(camera_fl), dm, out)
+        return out.numpy()
+
+    def imageprojection_backward(self, locs, image, camera_fl, depth_mask, grad_out):
+        l, im, dm, go = self._t(locs), self._t(image), self._t(depth_mask), self._t(grad_out)
+        dl, di = self.torch.zeros(l.shape), self.torch.zeros(im.shape)
+        self.ext.spn_imageprojection_backward(l, im, float(camera_fl), dm, go, dl, di)
+        return dl.numpy(), di.numpy()
 
 
 def grid_bounds_torch(locs, radius, max_grid_dim):

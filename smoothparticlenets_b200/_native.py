@@ -53,6 +53,10 @@ _SIGNATURES = {
                                   _vp, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "spnb_convsdf_backward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp, _vp, _i, _vp,
                                    _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),
+    "spnb_particleprojection_forward": (_i, [_vp, _i, _i, _f, _i, _i, _f, _f, _vp, _vp, _vp]),
+    "spnb_particleprojection_backward": (_i, [_vp, _i, _i, _f, _i, _i, _f, _f, _vp, _vp, _vp, _vp]),
+    "spnb_imageprojection_forward": (_i, [_vp, _vp, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp]),
+    "spnb_imageprojection_backward": (_i, [_vp, _vp, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "spnb_convsdf_backward_analytic": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp,
                                             _vp, _i, _vp, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp,
                                             _vp]),

@@ -19,7 +19,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB_PATH = os.environ.get("SPNB_LIB") or os.path.join(HERE, "libspnb.so")
 SOURCES = ["common.cu", "hashgrid.cu", "convsp.cu", "convsp_small.cu", "convsp_group.cu", "convsp_group_inst_fluid3.cu",
            "convsp_group_inst_fluid2.cu", "convsp_group_inst_single3.cu", "convsp_group_inst_single2.cu",
-           "convsp_wide.cu", "convsp_wide_mma.cu", "convsp_wide_bwd.cu", "convsdf.cu", "fluid_glue.cu"]
+           "convsp_wide.cu", "convsp_wide_mma.cu", "convsp_wide_bwd.cu", "convsdf.cu", "projection.cu", "fluid_glue.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -103,3 +103,15 @@ def fluid_cloud(seed, B, N, density=7640.0, D=3):
     locs = (r.rand(B, N, D) * L).astype(np.float32)
     vel = r.rand(B, N, D).astype(np.float32)
     return locs, vel, L
+
+
+def projection_case(seed=0, B=2, N=200, W=64, H=48, C=3, fl=40.0):
+    """Camera-space particles in front of, beside and behind a W x H camera, a depth mask that hides part of the
+    image (in the spirit of tests/test_particleprojection.py:84-116) and an image to sample."""
+    r = rng(seed)
+    locs = (r.rand(B, N, 3).astype(np.float32) - 0.5) * np.array([4, 3, 0], np.float32)
+    locs[..., 2] = r.rand(B, N).astype(np.float32) * 4 - 0.5  # some behind the camera
+    dm = np.full((B, H, W), np.finfo(np.float32).max, np.float32)
+    dm[0, H // 5:H * 3 // 5, W // 3:W * 3 // 4] = r.rand(H * 3 // 5 - H // 5, W * 3 // 4 - W // 3).astype(np.float32) * 3
+    image = r.rand(B, C, H, W).astype(np.float32)
+    return dict(locs=locs, depth_mask=dm, image=image, fl=np.float32(fl))

@@ -98,6 +98,20 @@ def convsdf_fixture(R, seed, D, ks):
     return out
 
 
+def projection_fixture(R, seed, std, scale):
+    c = cases.projection_case(seed)
+    fl = float(c["fl"])
+    out = dict(c)
+    out["std"], out["scale"] = np.float32(std), np.float32(scale)
+    out["pp_fwd"] = R.particleprojection_forward(c["locs"], fl, std, scale, c["depth_mask"])
+    out["pp_go"] = cases.rng(seed + 3).rand(*out["pp_fwd"].shape).astype(np.float32)
+    out["pp_dl"] = R.particleprojection_backward(c["locs"], fl, std, scale, c["depth_mask"], out["pp_go"])
+    out["ip_fwd"] = R.imageprojection_forward(c["locs"], c["image"], fl, c["depth_mask"])
+    out["ip_go"] = cases.rng(seed + 4).rand(*out["ip_fwd"].shape).astype(np.float32)
+    out["ip_dl"], out["ip_di"] = R.imageprojection_backward(c["locs"], c["image"], fl, c["depth_mask"], out["ip_go"])
+    return out
+
+
 def kernel_fixture():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
@@ -129,6 +143,8 @@ def main():
         "convsdf_3d": convsdf_fixture(R, 0, 3, (3, 1, 3)),
         "convsdf_2d": convsdf_fixture(R, 1, 2, (3, 3)),
         "convsdf_1d": convsdf_fixture(R, 2, 1, (3,)),
+        "projection_a": projection_fixture(R, 0, 2.5, 3.0),
+        "projection_b": projection_fixture(R, 1, 0.8, 1.0 / 0.06),
         "kernel_fn": kernel_fixture(),
     }
     for name, d in fx.items():

@@ -87,6 +87,21 @@ def test_golden_convsdf(oracle, name):
         bit_equal(dp[..., :D], g["dpt_" + t], "convsdf dposes translation")
 
 
+@pytest.mark.parametrize("name", ["projection_a", "projection_b"])
+def test_golden_projections(oracle, name):
+    """ParticleProjection / ImageProjection (common_funcs.h:979-1183) against vectors from the reference CPU build."""
+    g = load(name)
+    fl, std, scale = float(g["fl"]), float(g["std"]), float(g["scale"])
+    bit_equal(oracle.particleprojection_forward(g["locs"], fl, std, scale, g["depth_mask"]), g["pp_fwd"], "pp fwd")
+    bit_equal(oracle.particleprojection_backward(g["locs"], fl, std, scale, g["depth_mask"], g["pp_go"]), g["pp_dl"],
+              "pp dlocs")
+    bit_equal(oracle.imageprojection_forward(g["locs"], g["image"], fl, g["depth_mask"]), g["ip_fwd"], "ip fwd")
+    dl, di = oracle.imageprojection_backward(g["locs"], g["image"], fl, g["depth_mask"], g["ip_go"])
+    bit_equal(dl, g["ip_dl"], "ip dlocs")
+    bit_equal(di, g["ip_di"], "ip dimage")
+    assert (g["pp_fwd"] != 0).sum() > 100 and (g["ip_fwd"] != 0).sum() > 50
+
+
 def test_golden_kernel_table(oracle):
     """Kernel ids and formulas: the reference's KERNEL_NAMES / KERNEL_FN (kernels.py:123-131)
     against (a) the oracle's C table, (b) the product's Python table."""
@@ -180,6 +195,23 @@ def test_live_reference_agreement(oracle, ref_oracle):
         g1, g2 = C.convsdf_backward(*a, go, pose_grads=True), R.convsdf_backward(*a, go, pose_grads=True)
         bit_equal(g1[0], g2[0], "dlocs"), bit_equal(g1[1], g2[1], "dweight")
         bit_equal(g1[2][..., :D], g2[2][..., :D], "dposes translation")
+
+
+def test_live_reference_projections(oracle, ref_oracle):
+    """ParticleProjection / ImageProjection, fresh seeds and sizes, C restatement vs the compiled reference."""
+    for seed, (W, H), std in ((31, (40, 30), 1.3), (32, (33, 57), 3.0), (33, (8, 8), 5.0)):
+        c = cases.projection_case(seed, B=3, N=120, W=W, H=H, C=2, fl=25.0)
+        a = (c["locs"], 25.0, std, 2.0, c["depth_mask"])
+        fwd = oracle.particleprojection_forward(*a)
+        bit_equal(fwd, ref_oracle.particleprojection_forward(*a), "pp fwd")
+        go = cases.rng(seed).rand(*fwd.shape).astype(np.float32)
+        bit_equal(oracle.particleprojection_backward(*a, go), ref_oracle.particleprojection_backward(*a, go), "pp dl")
+        b = (c["locs"], c["image"], 25.0, c["depth_mask"])
+        f2 = oracle.imageprojection_forward(*b)
+        bit_equal(f2, ref_oracle.imageprojection_forward(*b), "ip fwd")
+        go = cases.rng(seed + 1).rand(*f2.shape).astype(np.float32)
+        for u, v in zip(oracle.imageprojection_backward(*b, go), ref_oracle.imageprojection_backward(*b, go)):
+            bit_equal(u, v, "ip grads")
 
 
 def test_selection_sort_is_a_per_cell_permutation_of_stable(oracle):
