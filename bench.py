@@ -304,9 +304,12 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO level
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        # NCCL logs, incl. the version banner of NCCL_DEBUG=VERSION/WARN, go to stdout by default, and NCCL honours
+        # NCCL_DEBUG_FILE only above the VERSION level: keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        if "NCCL_DEBUG_FILE" not in os.environ:
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     B, N = args.scenes, args.particles

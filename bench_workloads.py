@@ -194,8 +194,12 @@ def run_c5(args, ClockSampler):
     torch.cuda.set_device(local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29512")
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    # NCCL logs, incl. the version banner of NCCL_DEBUG=VERSION/WARN, go to stdout by default, and NCCL honours
+    # NCCL_DEBUG_FILE only above the VERSION level: keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
+    if "NCCL_DEBUG_FILE" not in os.environ:
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     N = args.particles if args.particles != 65536 else (1 << 24)
     if args.check:

@@ -5,7 +5,8 @@ Drop-in for python/SmoothParticleNets/convsp.py of the reference: same construct
 data, weight, bias; none for neighbors, convsp.py:198-203).  The legacy instance-style autograd
 Function of the reference (convsp.py:140-203) is a static new-style Function here.
 """
-import numbers  # noqa: F401
+import numbers
+import os  # noqa: F401
 
 import numpy as np
 import torch
@@ -60,7 +61,7 @@ class ConvSP(torch.nn.Module):
         # tile lists.  Measured on B200 (profiles/README.md) a single layer gains nothing from it -- the pack
         # pre-pass costs what the tile kernel saves -- so it is off by default; ConvSPGroup is where layers
         # sharing (locs, neighbors) win.
-        self.fast_path = False
+        self.fast_path = os.environ.get("SPNB_FAST_PATH", "0") == "1"
 
     def forward(self, locs, data, neighbors, qlocs=None):
         """locs BxNxD, data BxNxC, neighbors BxMxK (float indices, -1 terminated), qlocs BxMxD or
