@@ -591,6 +591,7 @@ int launch_convsp_wide_bwd(const float* qlocs, const float* locs, const float* d
     float* go_b = go_a + p.go_a;
     float* big = go_b + p.go_b;
     const bool need_x = dq || dl || dd;
+    const bool use_tc = K <= kGStage && ncells <= kMQ && getenv("SPNB_WIDE_TC") != nullptr;
     const int same = (dq != nullptr && dq == dl) ? 1 : 0;
     int launches = 0;
     if (need_x) {
@@ -628,11 +629,19 @@ int launch_convsp_wide_bwd(const float* qlocs, const float* locs, const float* d
             launches += 2;                                                                                        \
         }                                                                                                         \
         if (dw) {                                                                                                 \
-            SETATTR((k_wide_gather<DD, CC, true>), gsmem);                                                        \
             SETATTR(k_wide_dw_gemm<CC>, dwsmem);                                                                  \
-            k_wide_gather<DD, CC, true><<<ggrid, kGThreads, gsmem, stream>>>(qlocs, locs, data, neighbors, q_first, M, \
-                                                                            N, K, ncells, radius, kernel_size,    \
-                                                                            dilation, dis_norm, sp, big);         \
+            if (use_tc) {                                                                                         \
+                SETATTR((k_wide_gather_tc<DD, CC, true>), GatherTcLayout<CC>::bytes);                             \
+                k_wide_gather_tc<DD, CC, true><<<ggrid, kTcThreads, GatherTcLayout<CC>::bytes, stream>>>(          \
+                    qlocs, locs, data, neighbors, q_first, M, N, K, ncells, radius, kernel_size, dilation, dis_norm, \
+                    sp, big);                                                                                     \
+            } else {                                                                                              \
+                SETATTR((k_wide_gather<DD, CC, true>), gsmem);                                                    \
+                k_wide_gather<DD, CC, true><<<ggrid, kGThreads, gsmem, stream>>>(qlocs, locs, data, neighbors,    \
+                                                                                q_first, M, N, K, ncells, radius, \
+                                                                                kernel_size, dilation, dis_norm,  \
+                                                                                sp, big);                         \
+            }                                                                                                     \
             const int n_bt = nt * B;                                                                              \
             int ksplit = (2 * 148) / p.ncg;                                                                       \
             if (ksplit < 1) ksplit = 1;                                                                           \

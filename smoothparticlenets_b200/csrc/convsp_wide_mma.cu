@@ -217,6 +217,10 @@ int launch_convsp_wide_mma(const float* qlocs, const float* locs, const float* d
     int launches = 1;
     // measurement knob (bench.py): time the contraction alone, on whatever the image buffer holds
     const bool gemm_only = getenv("SPNB_WIDE_GEMM_ONLY") != nullptr;
+    // opt-in (environment SPNB_WIDE_TC): the gather as per-query tcgen05 GEMMs (k_wide_gather_tc), possible when a list
+    // fits one staging round and the kernel cells fit the 128 rows of an MMA.  Parity-tested, but measured 30 % slower
+    // than the CUDA-core gather on B200 (profiles/README.md), which therefore stays the default
+    const bool use_tc = K <= kGStage && ncells <= kMQ && getenv("SPNB_WIDE_TC") != nullptr;
     const size_t gsmem = C == 64 ? GatherLayout<3, 64>::bytes : GatherLayout<3, 32>::bytes;
     const size_t msmem = gemm_smem_bytes(C, Opad);
     // scenes are processed one after the other when B * tiles exceeds the chunk (the image buffer is per chunk)
@@ -239,10 +243,20 @@ int launch_convsp_wide_mma(const float* qlocs, const float* locs, const float* d
             set_error("spnb_convsp_forward_wide: shared memory not available");                                  \
             return -1;                                                                                            \
         }                                                                                                         \
-        if (!gemm_only)                                                                                           \
+        if (!gemm_only && use_tc) {                                                                               \
+            if (cudaFuncSetAttribute((k_wide_gather_tc<DD, CC, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)GatherTcLayout<CC>::bytes) != cudaSuccess) {                            \
+                set_error("spnb_convsp_forward_wide: shared memory not available");                              \
+                return -1;                                                                                        \
+            }                                                                                                     \
+            k_wide_gather_tc<DD, CC, false><<<ggrid, kTcThreads, GatherTcLayout<CC>::bytes, stream>>>(             \
+                qlocs, locs, data, neighbors, q_first, M, N, K, ncells, radius, kernel_size, dilation, dis_norm, sp, \
+                gimg);                                                                                            \
+        } else if (!gemm_only) {                                                                                  \
             k_wide_gather<DD, CC><<<ggrid, kGThreads, gsmem, stream>>>(qlocs, locs, data, neighbors, q_first, M, N, K, \
-                                                                      ncells, radius, kernel_size,                \
-                                                                      dilation, dis_norm, sp, gimg);              \
+                                                                      ncells, radius, kernel_size, dilation,      \
+                                                                      dis_norm, sp, gimg);                        \
+        }                                                                                                         \
         k_wide_gemm<CC><<<mgrid, kGemmThreads, msmem, stream>>>(gimg, wimg, bias, q_first, M, O, Opad, ncells, out); \
     } while (0)
         if (C == 64) {

@@ -88,6 +88,15 @@ __device__ __forceinline__ float to_tf32(float x)
     return __uint_as_float(r);
 }
 
+// hi + lo split without the (slow) cvt.rna.tf32: hi = x rounded to 10 mantissa bits with integer arithmetic (round half
+// up in magnitude), lo = x - hi exactly; lo is handed to the tensor core as it is (kind::tf32 ignores the low 13
+// mantissa bits: 2^-21 of x at most, the order of the dropped lo * lo term)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo)
+{
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = x - hi;
+}
+
 // ---- gather: G tiles as A operand images --------------------------------------------------------------------
 // gimg[tile][cell][part][ki][mi][8][4] floats: tile = 128 consecutive queries of the chunk, mi = 8-row group,
 // element (row = 8 mi + r, channel = 4 ki + e).  One CTA = 8 queries = one mi of one tile, one warp per query.
@@ -292,8 +301,10 @@ k_wide_gather(const float* __restrict__ qlocs, const float* __restrict__ locs, c
                 const int cl = t / (C / 16), ki = 4 * (t % (C / 16)) + kk;
                 const float4 v = *reinterpret_cast<const float4*>(s_G + (size_t)qq * L::QS + cl * L::CS + 4 * ki);
                 float4 hi, lo;
-                hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
-                lo.x = to_tf32(v.x - hi.x); lo.y = to_tf32(v.y - hi.y); lo.z = to_tf32(v.z - hi.z); lo.w = to_tf32(v.w - hi.w);
+                split_tf32(v.x, hi.x, lo.x);
+                split_tf32(v.y, hi.y, lo.y);
+                split_tf32(v.z, hi.z, lo.z);
+                split_tf32(v.w, hi.w, lo.w);
                 float* dst = gtile + (size_t)(cell0 + cl) * img_cell + ((size_t)ki * (kMQ / 8) + mi) * 32 + qq * 4;
                 *reinterpret_cast<float4*>(dst) = hi;
                 *reinterpret_cast<float4*>(dst + (size_t)kMQ * C) = lo;
@@ -306,14 +317,317 @@ k_wide_gather(const float* __restrict__ qlocs, const float* __restrict__ locs, c
             for (int t = warp; t < ncs * (C / 8) * 2; t += kTQ) {
                 const int qh = t & 1, ci = (t >> 1) % (C / 8), cl = (t >> 1) / (C / 8);
                 const float v = s_G[(size_t)(4 * qh + (lane & 3)) * L::QS + cl * L::CS + 8 * ci + (lane >> 2)];
-                const float hi = to_tf32(v);
+                float hi, lo;
+                split_tf32(v, hi, lo);
                 const int cell = cell0 + cl, cg = cell / CPG, rowgrp = (cell % CPG) * (C / 8) + ci, kq = 2 * mi + qh;
                 float* dst = ttile + (size_t)cg * ((size_t)2 * kMQ * kMQ) + ((size_t)kq * (kMQ / 8) + rowgrp) * 32 + lane;
                 dst[0] = hi;
-                dst[(size_t)kMQ * kMQ] = to_tf32(v - hi);
+                dst[(size_t)kMQ * kMQ] = lo;
             }
         }
         __syncthreads();
+    }
+}
+
+
+// ---- the gather on the tensor cores -----------------------------------------------------------------------------
+// Per query the gather IS a small GEMM: G[cell, c] = sum_j S[cell, j] * data[j, c] with S[cell, j] = W * norm of the
+// in-radius (cell, neighbour) pairs and 0 elsewhere: M = 128 kernel cells, N = C channels, K = the query's
+// (compacted) neighbours.  One CTA owns 8 queries (one 8-row group of an image tile):
+//   * each warp compacts one query's list (gather_stage);
+//   * per query (and 64 neighbours) all warps build the two operands in shared memory as the tensor core's K-major
+//     core-matrix images, split hi + lo TF32: A = S (a lane evaluates one (cell, neighbour) pair: exact fp32
+//     predicate, sph_fast weight; 32 lanes = one 128-byte core matrix, conflict-free stores), B = the neighbours'
+//     feature rows transposed; fence.proxy.async, then one thread issues the 3xTF32 tcgen05.mma chain into the
+//     query's own TMEM accumulator (8 x C columns = all of tensor memory at C = 64); the operands are double
+//     buffered, so the MMAs of query r run under the operand build of query r + 1;
+//   * epilogue: a thread = one kernel cell pulls its 8 queries' values out of TMEM and writes whole 128-byte core
+//     matrices of the operand image (T == false: rows = queries, K = channels; T == true: rows = (cell, channel),
+//     K = queries).
+// The sums differ from the reference's only in order (and by the 2^-22 relative lo*lo terms).
+constexpr int kTcK = 64;  // neighbours per operand build
+#ifndef SPNB_TC_THREADS
+#define SPNB_TC_THREADS 512
+#endif
+constexpr int kTcThreads = SPNB_TC_THREADS;  // one CTA per SM (all of tensor memory): the warps that hide the operand build's latency
+constexpr int kTcWarps = kTcThreads / 32;
+
+struct GatherTcSmem {
+    unsigned long long free_[2], done;
+    unsigned tmem_base;
+    int n[kTQ];
+    float4 qpos[kTQ];
+};
+
+template <int C>
+struct GatherTcLayout {
+    static constexpr int A_PART = kMQ * kTcK * 4;          // bytes of one part (hi or lo) of S
+    static constexpr int B_PART = C * kTcK * 4;
+    static constexpr int A_OFF = 0;                        // two buffers of [hi | lo]
+    static constexpr int B_OFF = 2 * 2 * A_PART;
+    static constexpr int NB_OFF = B_OFF + 2 * 2 * B_PART;  // staged neighbours: kTQ x kGStage float4
+    static constexpr int OFF_OFF = NB_OFF + kTQ * kGStage * 16;  // kernel-cell offsets: 128 float4
+    static constexpr int CTL_OFF = OFF_OFF + kMQ * 16;
+    static constexpr size_t bytes = CTL_OFF + sizeof(GatherTcSmem) + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld4_nowait(unsigned taddr, float* v)
+{
+    unsigned r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void tmem_ld8_nowait(unsigned taddr, float* v)
+{
+    unsigned r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int D, int C, bool T>
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_wide_gather_tc(const float* __restrict__ qlocs, const float* __restrict__ locs, const float* __restrict__ data,
+                 const float* __restrict__ neighbors, int q_first, int M, int N, int K, int ncells, float radius,
+                 const float* __restrict__ ksize, const float* __restrict__ dilation, int dis_norm, SphParams sp,
+                 float* __restrict__ gimg)
+{
+    using L = GatherTcLayout<C>;
+    extern __shared__ unsigned char s_dyn[];
+    unsigned char* s_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<size_t>(s_dyn) + 1023) & ~(size_t)1023);
+    float4* s_nb_all = reinterpret_cast<float4*>(s_raw + L::NB_OFF);
+    float4* s_off = reinterpret_cast<float4*>(s_raw + L::OFF_OFF);
+    GatherTcSmem* sm = reinterpret_cast<GatherTcSmem*>(s_raw + L::CTL_OFF);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    constexpr unsigned A_LBO = (kMQ / 8) * 128, A_SBO = 128, B_LBO = (C / 8) * 128, B_SBO = 128;
+    constexpr unsigned tmem_cols = kTQ * C;  // 512 or 256
+
+    // kernel shape, cull radius (common_funcs.h:481-485), the cells' offsets
+    int ks[D], half[D];
+    float dil[D];
+    float maxdil = dilation[0], maxks = ksize[0];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        ks[k] = (int)ksize[k];
+        half[k] = ((int)ksize[k]) / 2;
+        dil[k] = dilation[k];
+        if (dilation[k] > maxdil) maxdil = dilation[k];
+        if (ksize[k] > maxks) maxks = ksize[k];
+    }
+    const float nr = radius + ((int)maxks / 2) * maxdil * fast_root_dim(D);
+    const float cull2 = nr * nr, rad2 = radius * radius;
+    const SphF sf = {sp.H, 1.0f / sp.H, sp.H * sp.H};
+    const float wcoef = (float)(sp.w_expr == E_DSPIKY ? sp.w_coef / (double)sp.H : sp.w_coef);
+    if (tid < kMQ) {
+        float o[3] = {0.0f, 0.0f, 0.0f};
+        int rem = tid < ncells ? tid : 0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const int ik = rem % ks[k];
+            rem /= ks[k];
+            o[k] = (ik - half[k]) * dil[k];
+        }
+        s_off[tid] = make_float4(o[0], o[1], o[2], tid < ncells ? 1.0f : 0.0f);
+    }
+    if (tid == 0) {
+        mbar_init(&sm->free_[0], 1);
+        mbar_init(&sm->free_[1], 1);
+        mbar_init(&sm->done, 1);
+    }
+    if (warp == 0) tmem_alloc(&sm->tmem_base, tmem_cols);
+
+    // ---- warp r compacts the list of query r
+    const float* sl = locs + (size_t)b * N * D;
+    const float* sd = data + (size_t)b * N * C;
+    if (warp < kTQ) {
+        const int m = q_first + blockIdx.x * kTQ + warp;
+        int n = 0;
+        float x[3] = {0.0f, 0.0f, 0.0f};
+        if (m < M) {
+            const size_t q = (size_t)b * M + m;
+#pragma unroll
+            for (int k = 0; k < D; ++k) x[k] = qlocs[q * D + k];
+            bool ended = false;
+            n = gather_stage<D>(neighbors + q * K, K, 0, sl, x, cull2, s_nb_all + warp * kGStage, lane, ended);
+        }
+        if (lane == 0) {
+            sm->n[warp] = n;
+            sm->qpos[warp] = make_float4(x[0], x[1], x[2], 0.0f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = sm->tmem_base;
+
+    // ---- units of work: (query r, 64 neighbours)
+    int unit = 0;
+    for (int r = 0; r < kTQ; ++r) {
+        const int n_r = sm->n[r];
+        const float4 xq = sm->qpos[r];
+        const float4* nb = s_nb_all + r * kGStage;
+        for (int j0 = 0; j0 < n_r; j0 += kTcK, ++unit) {
+            const int buf = unit & 1;
+            const int cnt = min(kTcK, n_r - j0);
+            const int nkq = ((cnt + 7) >> 3) << 1;  // 4-neighbour groups, whole K steps of 8
+            if (unit >= 2) mbar_wait(&sm->free_[buf], (unsigned)((unit - 2) >> 1) & 1u);
+            float* a_hi = reinterpret_cast<float*>(s_raw + L::A_OFF + buf * 2 * L::A_PART);
+            float* a_lo = a_hi + L::A_PART / 4;
+            float* b_hi = reinterpret_cast<float*>(s_raw + L::B_OFF + buf * 2 * L::B_PART);
+            float* b_lo = b_hi + L::B_PART / 4;
+            // B = the neighbours' features: core matrix (kq, ci) = 8 channels x 4 neighbours; the global loads go first,
+            // their latency passes under the A build
+            constexpr int kBIter = (2 * (kTcK / 8) * (C / 8) + kTcWarps - 1) / kTcWarps;
+            float bv[kBIter];
+#pragma unroll
+            for (int u = 0; u < kBIter; ++u) {
+                const int it = warp + u * kTcWarps;
+                const int ci = it % (C / 8), kq = it / (C / 8);
+                const int c = 8 * ci + (lane >> 2), j = j0 + 4 * kq + (lane & 3);
+                bv[u] = (it < nkq * (C / 8) && j < n_r) ? __ldg(sd + (size_t)(int)nb[j].w * C + c) : 0.0f;
+            }
+            // A = S: core matrix (kq, mi) = 8 cells x 4 neighbours, lane = (cell & 7) * 4 + (j & 3)
+            for (int it = warp; it < nkq * (kMQ / 8); it += kTcWarps) {
+                const int mi = it & (kMQ / 8 - 1), kq = it / (kMQ / 8);
+                const int cell = 8 * mi + (lane >> 2), j = j0 + 4 * kq + (lane & 3);
+                const float4 off = s_off[cell];
+                float s = 0.0f;
+                if (j < n_r && off.w != 0.0f) {
+                    const float4 y = nb[j];
+                    const float xo[3] = {xq.x + off.x, xq.y + off.y, xq.z + off.z};
+                    const float yy[3] = {y.x, y.y, y.z};
+                    float d = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        const float t = xo[k] - yy[k];
+                        d += t * t;
+                    }
+                    if (d < rad2) {
+                        const float dist = sqrtf(d);  // exact: decides the d > H guard like the reference
+                        s = dist > sp.H ? 0.0f : sph_fast(sp.w_expr, dist, d, wcoef, sf);
+                        if (dis_norm && dist > 0.0f) s *= fast_rsqrt(d);
+                    }
+                }
+                float hi, lo;
+                split_tf32(s, hi, lo);
+                a_hi[it * 32 + lane] = hi;
+                a_lo[it * 32 + lane] = lo;
+            }
+            // B: the loads were issued before the A build
+#pragma unroll
+            for (int u = 0; u < kBIter; ++u) {
+                const int it = warp + u * kTcWarps;
+                if (it < nkq * (C / 8)) {
+                    float hi, lo;
+                    split_tf32(bv[u], hi, lo);
+                    b_hi[it * 32 + lane] = hi;
+                    b_lo[it * 32 + lane] = lo;
+                }
+            }
+            fence_proxy_async();  // the tensor core reads shared memory through the async proxy
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const unsigned idesc = umma_idesc_tf32(kMQ, C);
+                const unsigned acc = tmem + (unsigned)(r * C);
+                const unsigned ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+                for (int kk = 0; kk < (nkq >> 1); ++kk) {
+                    const unsigned ao = (unsigned)kk * 2u * A_LBO, bo = (unsigned)kk * 2u * B_LBO;
+                    const unsigned long long dah = umma_desc(ah + ao, A_LBO, A_SBO), dal = umma_desc(al + ao, A_LBO, A_SBO);
+                    const unsigned long long dbh = umma_desc(bh + bo, B_LBO, B_SBO), dbl = umma_desc(bl + bo, B_LBO, B_SBO);
+                    umma_tf32(acc, dal, dbh, idesc, (j0 > 0 || kk > 0) ? 1u : 0u);
+                    umma_tf32(acc, dah, dbl, idesc, 1u);
+                    umma_tf32(acc, dah, dbh, idesc, 1u);
+                }
+                umma_commit(&sm->free_[buf]);
+            }
+        }
+    }
+    if (tid == 0) umma_commit(&sm->done);  // arrives when every MMA above is complete
+    mbar_wait(&sm->done, 0);
+    tc_fence_after();
+
+    // ---- epilogue: thread = kernel cell (TMEM lane); warps w, w + 4, ... share a lane quarter
+    const int quarter = warp & 3, hsel = warp >> 2;
+    const int cell = quarter * 32 + lane;
+    const unsigned trow = tmem + ((unsigned)(quarter * 32) << 16);
+    const int tile = blockIdx.x / (kMQ / kTQ), mi = blockIdx.x % (kMQ / kTQ);
+    if (!T) {
+        const size_t img_cell = (size_t)2 * kMQ * C;
+        float* gtile = gimg + ((size_t)b * gridDim.x / (kMQ / kTQ) + tile) * ncells * img_cell;
+        for (int ki = hsel; ki < C / 4; ki += kTcWarps / 4) {
+            float v[kTQ][4];
+#pragma unroll
+            for (int q = 0; q < kTQ; ++q) {
+                if (sm->n[q] > 0) tmem_ld4_nowait(trow + (unsigned)(q * C + 4 * ki), v[q]);
+                else v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.0f;
+            }
+            tmem_wait_ld();
+            if (cell < ncells) {
+                float4* dst = reinterpret_cast<float4*>(gtile + (size_t)cell * img_cell + ((size_t)ki * (kMQ / 8) + mi) * 32);
+                float4* dst_lo = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + (size_t)kMQ * C);
+#pragma unroll
+                for (int q = 0; q < kTQ; ++q) {
+                    float4 hi, lo;
+                    split_tf32(v[q][0], hi.x, lo.x);
+                    split_tf32(v[q][1], hi.y, lo.y);
+                    split_tf32(v[q][2], hi.z, lo.z);
+                    split_tf32(v[q][3], hi.w, lo.w);
+                    dst[q] = hi;
+                    dst_lo[q] = lo;
+                }
+            }
+        }
+    } else {
+        constexpr int CPG = kMQ / C;
+        const int ncg = (ncells + CPG - 1) / CPG;
+        float* ttile = gimg + ((size_t)b * gridDim.x / (kMQ / kTQ) + tile) * ncg * ((size_t)2 * kMQ * kMQ);
+        const int cg = cell / CPG;
+        // core matrix (ci, query half qh): 8 channels x 4 queries
+        for (int ci = hsel; ci < C / 8; ci += kTcWarps / 4) {
+#pragma unroll
+            for (int qh = 0; qh < 2; ++qh) {
+                float v[4][8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int q = 4 * qh + e;
+                    if (sm->n[q] > 0) tmem_ld8_nowait(trow + (unsigned)(q * C + 8 * ci), v[e]);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[e][i] = 0.0f;
+                    }
+                }
+                tmem_wait_ld();
+                if (cell < ncells) {
+                    const int rowgrp = (cell % CPG) * (C / 8) + ci, kq = 2 * mi + qh;
+                    float4* dst = reinterpret_cast<float4*>(ttile + (size_t)cg * ((size_t)2 * kMQ * kMQ) +
+                                                            ((size_t)kq * (kMQ / 8) + rowgrp) * 32);
+                    float4* dst_lo = reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + (size_t)kMQ * kMQ);
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        float4 hi, lo;
+                        split_tf32(v[0][rr], hi.x, lo.x);
+                        split_tf32(v[1][rr], hi.y, lo.y);
+                        split_tf32(v[2][rr], hi.z, lo.z);
+                        split_tf32(v[3][rr], hi.w, lo.w);
+                        dst[rr] = hi;
+                        dst_lo[rr] = lo;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, tmem_cols);
     }
 }
 

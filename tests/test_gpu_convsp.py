@@ -344,6 +344,16 @@ def test_wide_channel_backward(spn, oracle, D, ks, C, O, fn, dn, alias, K):
     assert float((dt2.grad - dt.grad).abs().max()) <= 1e-5 * float(dt.grad.abs().max())
 
 
+def test_wide_gather_on_tensor_cores(spn, oracle, monkeypatch):
+    """SPNB_WIDE_TC=1: the gather itself as per-query tcgen05 GEMMs (k_wide_gather_tc: S[cell, neighbour] x
+    features, accumulators of 8 queries in tensor memory) -- an opt-in alternative to the CUDA-core gather; same
+    forward and the same four gradients."""
+    monkeypatch.setenv("SPNB_WIDE_TC", "1")
+    test_wide_channel_forward(spn, oracle, 3, (3, 3, 3), 64, 64, "spiky", 0)
+    test_wide_channel_backward(spn, oracle, 3, (3, 3, 3), 64, 64, "spiky", 0, False, 64)
+    test_wide_channel_backward(spn, oracle, 3, (5, 1, 3), 32, 16, "dspiky", 1, True, 48)
+
+
 def test_full_size_properties(spn):
     """BASELINE.json config 2 size (8 x 65536 particles): size-independent properties of ConvSP --
     the `constant` kernel with unit data counts neighbours, outputs are linear in the data, the fused
