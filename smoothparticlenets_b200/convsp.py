@@ -56,12 +56,12 @@ class ConvSP(torch.nn.Module):
         # Kept for attribute compatibility (convsp.py:85-86); unused.
         self.nshared_device_mem = -1
         self.device_id = -1
-        # extension: True routes a kernel_size-1 layer with up to 4 input channels through the single-layer
-        # signature of the tile kernels (pack pre-pass + k_tile_fwd / k_tile_bwd) when the neighbour tensor carries
-        # tile lists.  Measured on B200 (profiles/README.md) a single layer gains nothing from it -- the pack
-        # pre-pass costs what the tile kernel saves -- so it is off by default; ConvSPGroup is where layers
-        # sharing (locs, neighbors) win.
-        self.fast_path = os.environ.get("SPNB_FAST_PATH", "0") == "1"
+        # True (default; environment SPNB_FAST_PATH=0 turns it off) routes a kernel_size-1 layer with up to 4 input
+        # channels and no trainable weights through the single-layer signature of the tile kernels (pack pre-pass +
+        # k_tile_fwd / k_tile_bwd) when the neighbour tensor carries tile lists: same values within fp32 rounding.
+        # Measured on B200 (profiles/README.md): the per-layer fluid step 6.86 -> 6.53 ms; a tile kernel costs the
+        # same for one layer as for six, so ConvSPGroup is where layers sharing (locs, neighbors) really win.
+        self.fast_path = os.environ.get("SPNB_FAST_PATH", "1") != "0"
 
     def forward(self, locs, data, neighbors, qlocs=None):
         """locs BxNxD, data BxNxC, neighbors BxMxK (float indices, -1 terminated), qlocs BxMxD or
