@@ -20,8 +20,8 @@
 //   k_wide_go_images   go -> the A operand of the dG GEMM (rows q, K = o) and the B operand of the dweight GEMM
 //                      (rows o, K = q), both as hi + lo TF32 terms in the tensor core's shared-memory image;
 //   k_wide_dg_gemm     per tile: go image resident, the transposed weight images streamed cell by cell with TMA
-//                      bulk copies, 3xTF32 tcgen05.mma into alternating TMEM accumulators, epilogue warps store
-//                      dG[q][cell][c] rows;
+//                      bulk copies, 3xTF32 tcgen05.mma into alternating TMEM accumulators, epilogue warps transpose 32 x C blocks
+//                      through shared memory and store whole rows of dG[tile][cell][q][c];
 //   k_wide_scatter     one warp per query, one kernel cell per lane with its dG row in registers: the channel dot
 //                      product for the position gradients is C FMAs against the neighbour's broadcast feature
 //                      row; ddata goes through the lanes-as-channels view of the same dG tile in shared memory
@@ -115,7 +115,7 @@ k_wide_dg_gemm(const float* __restrict__ goA, const float* __restrict__ wimg_t, 
     const int STAGE = 2 * B_BYTES;
     unsigned char* s_a = s_raw;                    // [A hi | A lo]
     unsigned char* s_b = s_raw + 2 * (size_t)A_BYTES;  // two stages of [B hi | B lo]
-    DgSmem* sm = reinterpret_cast<DgSmem*>(s_b + 2 * (size_t)STAGE);
+    DgSmem* sm = reinterpret_cast<DgSmem*>(s_b + 2 * (size_t)STAGE + (size_t)4 * 32 * (C + 4) * 4);  // after the epilogue's staging tiles
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t bt = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
     constexpr unsigned tmem_cols = 2 * C <= 64 ? 64u : 128u;
@@ -178,23 +178,36 @@ k_wide_dg_gemm(const float* __restrict__ goA, const float* __restrict__ wimg_t, 
             __syncwarp();
         }
     } else {
+        // accumulator rows (thread = query) -> this warp's staging tile in shared memory (row stride C + 4 floats:
+        // conflict-free 128-bit stores), read back with the lanes along the rows, so that every global store of the
+        // warp covers two whole 256-byte rows of dG[tile][cell][query][c]
         const int quarter = warp & 3;
-        float* qrow = dgbuf + (bt * kMQ + (size_t)(quarter * 32 + lane)) * ncells * C;
+        constexpr int RS = C + 4;
+        float* stage = reinterpret_cast<float*>(s_b + 2 * (size_t)STAGE) + (size_t)quarter * 32 * RS;
+        float* gdst = dgbuf + (bt * ncells * kMQ + (size_t)quarter * 32) * C;  // + cell * kMQ * C
         for (int cell = 0; cell < ncells; ++cell) {
             const int fb = cell & 1;
             mbar_wait(&sm->free_[fb], (unsigned)(cell >> 1) & 1u);
             tc_fence_after();
+            __syncwarp();  // the previous cell's read-back is complete
 #pragma unroll
             for (int g = 0; g < C / 32; ++g) {
                 float v[32];
                 tmem_ld32(tmem + ((unsigned)(quarter * 32) << 16) + (unsigned)(fb * C + g * 32), v);
-                float4* dst = reinterpret_cast<float4*>(qrow + (size_t)cell * C + g * 32);
+                float4* row = reinterpret_cast<float4*>(stage + (size_t)lane * RS + g * 32);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                for (int i = 0; i < 8; ++i) row[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_(&sm->acc_free[fb]);
+            constexpr int PPR = C / 4;  // 16-byte pieces per row
+            float4* out4 = reinterpret_cast<float4*>(gdst + (size_t)cell * kMQ * C);
+#pragma unroll
+            for (int t = 0; t < PPR; ++t) {
+                const int idx = t * 32 + lane, r = idx / PPR, pc = idx % PPR;
+                out4[idx] = *reinterpret_cast<const float4*>(stage + (size_t)r * RS + 4 * pc);
+            }
         }
     }
     __syncthreads();
@@ -255,8 +268,9 @@ k_wide_scatter(const float* __restrict__ qlocs, const float* __restrict__ locs, 
     float* dlb = dl ? dl + (size_t)b * N * D : nullptr;
     float* ddb = dd ? dd + (size_t)b * N * C : nullptr;
     const bool want_locs = dq != nullptr || dl != nullptr;
-    // dG rows of this query: [cell][c]
-    const float* dgq = dgbuf + (((size_t)b * gridDim.x * kTQ) + (size_t)blockIdx.x * kTQ + warp) * ncells * C;
+    // dG of this query: dgbuf[tile][cell][query in tile][c]
+    const int qt = blockIdx.x * kTQ + warp;  // query within the chunk
+    const float* dgq = dgbuf + (((size_t)b * (gridDim.x * kTQ / kMQ) + qt / kMQ) * ncells * kMQ + (qt % kMQ)) * C;
 
     const bool one_round = K <= kGStage;
     int n_staged = 0;
@@ -284,7 +298,7 @@ k_wide_scatter(const float* __restrict__ qlocs, const float* __restrict__ locs, 
         float dg[C];
         __syncwarp();
         {
-            const float4* src = reinterpret_cast<const float4*>(dgq + (size_t)(cell0 + (valid ? lane : 0)) * C);
+            const float4* src = reinterpret_cast<const float4*>(dgq + (size_t)(cell0 + (valid ? lane : 0)) * kMQ * C);
             float4* g4 = reinterpret_cast<float4*>(Gq + (size_t)lane * L::CS);
 #pragma unroll
             for (int c4 = 0; c4 < C / 4; ++c4) {
@@ -537,7 +551,7 @@ k_wide_dw_gemm(const float* __restrict__ gimg_t, const float* __restrict__ goB, 
 
 static size_t dg_smem_bytes(int C, int Opad)
 {
-    return (size_t)2 * kMQ * Opad * 4 + (size_t)2 * 2 * C * Opad * 4 + sizeof(DgSmem) + 64;
+    return (size_t)2 * kMQ * Opad * 4 + (size_t)2 * 2 * C * Opad * 4 + (size_t)4 * 32 * (C + 4) * 4 + sizeof(DgSmem) + 64;
 }
 static size_t dw_smem_bytes(int Opad)
 {
