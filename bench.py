@@ -129,8 +129,7 @@ def run_reference_arm(args):
     # load the reference's compiled CPU extension (oracle/_ref) in THIS process too: the pool workers are forked
     # from it, and the driver's record of loaded native libraries then shows what the arm actually ran
     from oracle import cpu_modules as cm
-    parent_kind = cm.backend().kind
-    _cpu_scene_step((99, 256))
+    parent_kind = cm.backend().kind  # (no autograd here: its threads would not survive the fork below)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for w in range(args.warmup):

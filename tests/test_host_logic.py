@@ -139,3 +139,20 @@ def test_tile_list_layout_mirror_matches_library(spn):
     assert b"null pointer" in L.spnb_last_error()
     assert L.spnb_pbf_stage1_forward(None, None, None, None, None, None, None, 10, 3, 1.0, 1.0, None) == 0
     assert b"bad arguments" in L.spnb_last_error()
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the reference's CPU functions on the host cores, forked workers) on a tiny sample:
+    exactly one JSON line on stdout with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--cpu-particles", "512"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.split("\n") if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["unit"] == "particles/s"
