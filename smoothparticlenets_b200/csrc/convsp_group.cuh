@@ -911,6 +911,9 @@ inline bool launched(const char* what)
 template <typename KernelT>
 inline bool allow_smem(KernelT* kernel, size_t bytes)
 {
+    // as many CTAs per SM as the shared memory allows: ask for the largest carve-out (the driver's default choice left
+    // the 3-plane backward kernels at 3 CTAs per SM where 4 fit)
+    cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     // static + dynamic shared memory above 48 KB needs the opt-in
     if (bytes + 1024 > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

@@ -8,7 +8,7 @@ the product path calls it.
 import numpy as np
 
 TILE_Q = 64
-TILE_CAP = 1024
+TILE_CAP = 1016
 DESC_INTS = 32
 MAX_RANGES = 9
 OCTILES = 8
