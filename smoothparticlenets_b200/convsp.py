@@ -57,8 +57,9 @@ class ConvSP(torch.nn.Module):
         self.nshared_device_mem = -1
         self.device_id = -1
         # True (default; environment SPNB_FAST_PATH=0 turns it off) routes a kernel_size-1 layer with up to 4 input
-        # channels and no trainable weights through the single-layer signature of the tile kernels (pack pre-pass +
-        # k_tile_fwd / k_tile_bwd) when the neighbour tensor carries tile lists: same values within fp32 rounding.
+        # channels through the single-layer signature of the tile kernels (pack pre-pass + k_tile_fwd / k_tile_bwd) when
+        # the neighbour tensor carries tile lists: same values within fp32 rounding; d(weight) = go^T T comes from one
+        # more fused forward pass with identity weights (convsp_group.py).
         # Measured on B200 (profiles/README.md): the per-layer fluid step 6.86 -> 6.53 ms; a tile kernel costs the
         # same for one layer as for six, so ConvSPGroup is where layers sharing (locs, neighbors) really win.
         self.fast_path = os.environ.get("SPNB_FAST_PATH", "1") != "0"
@@ -82,7 +83,7 @@ class ConvSP(torch.nn.Module):
         if (sc is not None and sc.tiles is not None and self.ncells == 1 and self.nchannels <= 4
                 and self.fast_path):
             # kernel_size 1 on lists that carry tile lists: the single-layer signature of the tile kernels
-            # (csrc/convsp_group.cuh) -- same values within fp32 rounding, no d(weight)
+            # (csrc/convsp_group.cuh) -- same values within fp32 rounding
             from .convsp_group import group_apply
             out = group_apply([self], locs, [data], neighbors)
             if out is not None:

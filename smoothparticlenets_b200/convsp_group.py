@@ -8,11 +8,16 @@ data_b, ...], neighbors)`` returns exactly what ``[layer_a(locs, data_a, neighbo
 (same values within fp32 rounding, same gradients), but walks the lists once per group.
 
 Requirements for the fused path: every layer has kernel_size 1, the same ndim and radius, no query
-locations (the particles are their own queries), no trainable weights that need gradients, and the
+locations (the particles are their own queries), and the
 layer list is one of the compiled-in signatures (csrc/convsp_group_inst_*.cu: the groups of the fluid
 step, and ANY single layer with up to 4 input channels).  Anything else silently runs the ordinary
 per-layer path, so the module is always safe to use.  A data entry may be None: a one-channel layer
 whose data is all ones (density, neighbour count) then reads no data at all.
+
+Trainable weights: d(weight) of a kernel_size-1 layer is go^T T with T[i, c] = sum_j W * norm * data[j, c], the
+quantity the forward accumulates before it applies the weights.  The backward obtains T from one more pass of
+the same fused forward with identity weights and contracts it with grad_output (a [O x BN] x [BN x C] product),
+so layers with ``with_params=True`` fuse as well (reference formula: common_funcs.h:542-547).
 """
 import ctypes
 
@@ -63,11 +68,8 @@ class ConvSPGroup(torch.nn.Module):
 
 def group_apply(layers, locs, datas, neighbors):
     """The fused evaluation of `layers` (all kernel_size 1, same ndim and radius) on (locs, neighbors), or None when
-    it does not apply: CPU tensors, separate query locations, weights that need gradients (d(weight) is only
-    produced by the per-layer kernels), or a channel layout that is not compiled in."""
+    it does not apply: CPU tensors, separate query locations, or a channel layout that is not compiled in."""
     if not (locs.is_cuda and neighbors.dim() == 3 and neighbors.shape[1] == locs.shape[1]):
-        return None
-    if torch.is_grad_enabled() and any(l.weight.requires_grad for l in layers):
         return None
     locs_c = locs.contiguous()
     datas_c = [None if d is None else d.contiguous() for d in datas]
@@ -161,5 +163,24 @@ class _ConvSPGroupFunction(torch.autograd.Function):
                       "spnb_convsp_group_backward")
         need_data = ctx.needs_input_grad[5:5 + n]
         ddatas = [g if need_data[i] else None for i, g in enumerate(ddatas)]
+        need_w = ctx.needs_input_grad[5 + n:5 + 2 * n]
+        dweights = [None] * n
+        if any(need_w):
+            # T_l[i, c] = sum_j W * norm * data_l[j, c]: the fused forward once more, with identity weights
+            eyes = [torch.eye(c[2], device=dev, dtype=torch.float32).reshape(c[2], c[2], 1).contiguous() for c in cfg]
+            zeros = [torch.zeros(c[2], device=dev, dtype=torch.float32) for c in cfg]
+            cfg_t = tuple((fn, dn, C, C) for fn, dn, C, O in cfg)
+            ts = [torch.empty(B, N, c[2], device=dev, dtype=torch.float32) for c in cfg]
+            arr_t = _layer_array(locs, datas, eyes, zeros, cfg_t, outs=ts)
+            wsf = L.spnb_convsp_group_workspace_bytes(nat.ptr(locs), B, N, D, radius, n, arr_t, 0)
+            wst = torch.empty((wsf + 3) // 4, device=dev, dtype=torch.float32)
+            with torch.cuda.device(dev):
+                nat.check(L.spnb_convsp_group_forward(nat.ptr(locs), nat.ptr(neighbors), B, N, D, K, radius, n,
+                                                      arr_t, nat.ptr(wst), wsf, nat.ptr(ctx.tiles), nat.stream()),
+                          "spnb_convsp_group_forward (d(weight) pass)")
+            for i in range(n):
+                if need_w[i]:
+                    dweights[i] = torch.einsum("bno,bnc->oc", gos[i], ts[i]).unsqueeze(-1)
         dbias = [gos[i].sum(1).sum(0) if ctx.needs_input_grad[5 + 2 * n + i] else None for i in range(n)]
-        return (dlocs if need_locs else None, None, None, None, None) + tuple(ddatas) + (None,) * n + tuple(dbias)
+        return ((dlocs if need_locs else None, None, None, None, None) + tuple(ddatas) + tuple(dweights) +
+                tuple(dbias))

@@ -317,3 +317,57 @@ def test_single_layer_fast_path_option(spn, oracle):
             out.backward(gu.dev(go))
             close(lt.grad, dq.astype(np.float64) + dl, "%s fast=%s dlocs" % (kernel, fast), k=4)
             close(dt.grad, dd, "%s fast=%s ddata" % (kernel, fast), k=4)
+
+
+def test_trainable_weights_fuse(spn, oracle):
+    """Layers with with_params=True (the ConvSP default) take the fused path too: d(weight) = go^T T, with T from one
+    more pass of the fused forward with identity weights (common_funcs.h:542-547 is the reference's per-term
+    formula).  Checked for a single layer (the per-layer fast path) and for a two-layer group that is not one of
+    the fluid signatures' weight shapes (3 -> 5 and 1 -> 2 outputs), against the oracle and float64."""
+    from test_gpu_parity_configs import closer_than_reference, convsp_float64
+    B, N, D, R = 2, 1200, 3, 0.1
+    locs, vel, _ = cases.fluid_cloud(41, B, N)
+    coll = spn.ParticleCollision(D, R, include_self=False).cuda()
+    sl, sv, idxs, nb = coll(gu.dev(locs), gu.dev(vel))
+    nl, nv, nbh = gu.host(sl), gu.host(sv), gu.host(nb)
+    one3 = np.ones(3, np.float32)
+    r = cases.rng(2)
+    # --- single layer, default construction (trainable weight and bias)
+    conv = spn.ConvSP(3, 5, D, 1, 1, R, dis_norm=False, kernel_fn="spiky").cuda()
+    w, b = (r.rand(5, 3, 1) - 0.3).astype(np.float32), r.rand(5).astype(np.float32)
+    conv.weight.data.copy_(gu.dev(w))
+    conv.bias.data.copy_(gu.dev(b))
+    go = r.rand(B, N, 5).astype(np.float32)
+    n0 = nat.lib().spnb_launch_count()
+    out = conv(sl, sv, nb)
+    assert nat.lib().spnb_launch_count() - n0 == 2, "pack + tile kernel"
+    n0 = nat.lib().spnb_launch_count()
+    out.backward(gu.dev(go))
+    assert nat.lib().spnb_launch_count() - n0 == 4, "backward pack + kernel, identity-weight forward pack + kernel"
+    close(out, oracle.convsp_forward(nl, nl, nv, nbh, w, b, R, one3, one3, 0, "spiky"), "fwd")
+    _, _, _, dw, db = oracle.convsp_backward(nl, nl, nv, nbh, w, b, R, one3, one3, 0, "spiky", go)
+    _, w64 = convsp_float64(spn, nl, nl, nv, nbh, w, b, go, R, (1, 1, 1), [1.0] * 3, 0, "spiky")
+    closer_than_reference(gu.host(conv.weight.grad), dw, w64, "single-layer dweight")
+    close(conv.bias.grad, db, "dbias", k=4)
+    # --- a group: 3 -> 5 on the velocities and 1 -> 2 on implicit ones, both trainable
+    dens = spn.ConvSP(1, 2, D, 1, 1, R, dis_norm=False, kernel_fn="spiky").cuda()
+    w2, b2 = r.rand(2, 1, 1).astype(np.float32), r.rand(2).astype(np.float32)
+    dens.weight.data.copy_(gu.dev(w2))
+    dens.bias.data.copy_(gu.dev(b2))
+    conv.zero_grad()
+    group = spn.ConvSPGroup([conv, dens])
+    go2 = r.rand(B, N, 2).astype(np.float32)
+    lt = sl.detach().clone().requires_grad_(True)
+    n0 = nat.lib().spnb_launch_count()
+    o1, o2 = group(lt, [sv, None], nb)
+    assert nat.lib().spnb_launch_count() - n0 == 2, "one fused pass for both layers (compiled two-layer signature)"
+    (o1 * gu.dev(go)).sum().add((o2 * gu.dev(go2)).sum()).backward()
+    ones = np.ones((B, N, 1), np.float32)
+    _, _, _, dwd, dbd = oracle.convsp_backward(nl, nl, ones, nbh, w2, b2, R, one3, one3, 0, "spiky", go2)
+    _, wd64 = convsp_float64(spn, nl, nl, ones, nbh, w2, b2, go2, R, (1, 1, 1), [1.0] * 3, 0, "spiky")
+    closer_than_reference(gu.host(conv.weight.grad), dw, w64, "group dweight (layer 1)")
+    closer_than_reference(gu.host(dens.weight.grad), dwd, wd64, "group dweight (layer 2)")
+    close(dens.bias.grad, dbd, "group dbias", k=4)
+    dq1, dl1, _, _, _ = oracle.convsp_backward(nl, nl, nv, nbh, w, b, R, one3, one3, 0, "spiky", go)
+    dq2, dl2, _, _, _ = oracle.convsp_backward(nl, nl, ones, nbh, w2, b2, R, one3, one3, 0, "spiky", go2)
+    close(lt.grad, dq1.astype(np.float64) + dl1 + dq2 + dl2, "group dlocs", k=8)
