@@ -26,6 +26,55 @@ import torch.distributed as dist
 from .scene_parallel import HaloPlan, _HaloRows
 
 
+class _PermuteRows(torch.autograd.Function):
+    """y = x[idx] (gather) or y[idx] = x (scatter) for a PERMUTATION idx of the rows of a [n, W] float32 CUDA tensor,
+    through the library's row-permutation kernel (spnb_reorder_data, HBM-bound) instead of torch's advanced indexing
+    (whose gather / index_put backward run at a few per cent of the memory bandwidth at 2^24 rows).  The backward of
+    a permutation is the opposite mode with the same indices -- nothing is accumulated."""
+
+    @staticmethod
+    def forward(ctx, x, idx_f, gather):
+        ctx.save_for_backward(idx_f)
+        ctx.gather = gather
+        return _reorder_rows(x, idx_f, 0 if gather else 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx_f,) = ctx.saved_tensors
+        return _reorder_rows(g.contiguous(), idx_f, 1 if ctx.gather else 0), None, None
+
+
+def _reorder_rows(x, idx_f, reverse):
+    from . import _native as nat
+    n, W = x.shape
+    out = torch.empty_like(x)
+    if n == 0:
+        return out
+    with torch.cuda.device(x.device):
+        nat.check(nat.lib().spnb_reorder_data(nat.ptr(x), None, nat.ptr(idx_f), nat.ptr(out), None, 1, n, W, 0, reverse,
+                                              nat.stream()), "spnb_reorder_data")
+    return out
+
+
+def permute_rows(x, idx, gather=True):
+    """x [n, W] -> x[idx] (gather) or the tensor y with y[idx] = x (scatter); idx: int64 permutation of 0..n-1."""
+    if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and 0 < x.shape[0] <= (1 << 24) and x.shape[0] == idx.shape[0]:
+        return _PermuteRows.apply(x.contiguous(), idx.to(torch.float32), gather)
+    if gather:
+        return x[idx]
+    out = torch.empty_like(x)
+    out[idx] = x
+    return out
+
+
+def _argsort(keys):
+    """Stable ascending argsort of non-negative int64 keys; 32-bit keys halve the radix passes when they fit."""
+    if keys.numel() and keys.is_cuda and int(keys.numel()) < (1 << 31):
+        return torch.argsort(keys.to(torch.int32), stable=True) if bool((keys.max() < (1 << 31)).item()) else \
+            torch.argsort(keys, stable=True)
+    return torch.argsort(keys, stable=True)
+
+
 class _AllToAllRows(torch.autograd.Function):
     """rows [n, W] split by `send` counts -> rows received from every rank (`recv` counts); backward: the reverse."""
 
@@ -110,30 +159,37 @@ class SlabScene(object):
             raise ValueError("degenerate grid: all particles share their first coordinate")
         rt = torch.full((), radius, device=dev, dtype=torch.float32)
         layer = torch.trunc((locs.detach()[0, :, 0] - low[0, 0]) / rt).clamp_(0, nlayers - 1).to(torch.int64)
-        hist = torch.bincount(layer, minlength=nlayers).to(torch.int64)
+        hist_local = torch.bincount(layer, minlength=nlayers).to(torch.int64)
+        hist = hist_local.clone()
         dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=g)
         cuts = layer_cuts(hist.tolist(), R)               # host sync: R+1 numbers decide the decomposition
         self.cuts = cuts
         cut_t = torch.tensor(cuts[1:-1], device=dev, dtype=torch.int64)
         # 3. bucket exchange
-        dest = torch.bucketize(layer, cut_t, right=True)
-        order = torch.argsort(dest, stable=True)
-        send = torch.bincount(dest, minlength=R).tolist()
+        hl = hist_local.tolist()
+        send = [int(sum(hl[cuts[r]:cuts[r + 1]])) for r in range(R)]
+        if R == 1:
+            order = torch.arange(locs.shape[1], device=dev)
+        else:
+            dest = torch.bucketize(layer, cut_t, right=True)
+            order = _argsort(dest)
         recv_t = torch.empty(R, dtype=torch.int64, device=dev)
         dist.all_to_all_single(recv_t, torch.tensor(send, device=dev, dtype=torch.int64), group=g)
         recv = recv_t.tolist()
         self._a2a = (order, send, recv, locs.shape[1])
         C = 0 if data is None else data.shape[2]
         cols = [locs[0]] + ([data[0]] if data is not None else [])
-        rows = torch.cat(cols, 1)[order]
+        rows = torch.cat(cols, 1)
+        if R > 1:
+            rows = permute_rows(rows, order)
         got = _AllToAllRows.apply(rows, send, recv, g)
         own_gid = torch.empty(sum(recv), dtype=torch.int64, device=dev)
         dist.all_to_all_single(own_gid, gid[order].contiguous(), recv, send, group=g)
         own_layer = torch.empty(sum(recv), dtype=torch.int64, device=dev)
         dist.all_to_all_single(own_layer, layer[order].contiguous(), recv, send, group=g)
         # own block in global-id order (the stable sort by cell then reproduces the global order inside every cell)
-        by_gid = torch.argsort(own_gid)
-        got, own_gid, own_layer = got[by_gid], own_gid[by_gid], own_layer[by_gid]
+        by_gid = _argsort(own_gid)
+        got, own_gid, own_layer = permute_rows(got, by_gid), own_gid[by_gid], own_layer[by_gid]
         self._by_gid = by_gid
         m = got.shape[0]
         # 4. halo of positions: my first layer -> previous rank, my last layer -> next rank
@@ -162,8 +218,12 @@ class SlabScene(object):
         # 5. the extended set in global-id order -> ParticleCollision with the global bounds
         ext_pos = torch.cat([left[:, :D].float(), pos, right[:, :D].float()], 0)
         ext_gid = torch.cat([left[:, D].long(), own_gid, right[:, D].long()], 0)
-        eorder = torch.argsort(ext_gid)
-        ext_sorted_in = ext_pos[eorder].unsqueeze(0).contiguous()
+        if nl == 0 and nr == 0:
+            eorder = torch.arange(m, device=dev)           # the own block is in global-id order already
+            ext_sorted_in = ext_pos.unsqueeze(0).contiguous()
+        else:
+            eorder = _argsort(ext_gid)
+            ext_sorted_in = permute_rows(ext_pos, eorder).unsqueeze(0).contiguous()
         res = self.coll(ext_sorted_in, query_range=(nl, nl + m), bounds=(low, gd))
         ext_locs, idxs, neighbors = res[0], res[-2], res[-1]
         perm = eorder[idxs[0].long()]                    # cell-sorted position -> index into [left | own | right]
@@ -180,7 +240,7 @@ class SlabScene(object):
                              recvs=([(self.rank - 1, 0, nl)] if has_prev else []) +
                                    ([(self.rank + 1, nl + m, nl + m + nr)] if has_next else []),
                              group=g)
-        own_rows = got[own_sel]                          # differentiable: through the all_to_all back to the inputs
+        own_rows = permute_rows(got, own_sel)            # differentiable: through the all_to_all back to the inputs
         self.own_locs = own_rows[:, :D].unsqueeze(0)
         own_data = own_rows[:, D:D + C].unsqueeze(0) if C else None
         return self.own_locs, own_data, self.own_gid, neighbors
@@ -201,13 +261,9 @@ class SlabScene(object):
         """[1, m, C] rows in the own order -> [1, n, C] rows of the particles this rank contributed, in the order
         it contributed them (the inverse of steps 3-5; differentiable)."""
         order, send, recv, n = self._a2a
-        inv_sel = torch.empty_like(self._own_sel)
-        inv_sel[self._own_sel] = torch.arange(self.m, device=x_own.device)
-        rows = x_own[0][inv_sel]                         # gid order
-        inv_gid = torch.empty_like(self._by_gid)
-        inv_gid[self._by_gid] = torch.arange(self.m, device=x_own.device)
-        rows = rows[inv_gid]                             # arrival order of the all_to_all
+        rows = permute_rows(x_own[0], self._own_sel, gather=False)   # gid order: rows[own_sel[k]] = x[k]
+        rows = permute_rows(rows, self._by_gid, gather=False)        # arrival order of the all_to_all
         back = _AllToAllRows.apply(rows, recv, send, self.group)
-        out = torch.empty_like(back)
-        out[order] = back
-        return out.unsqueeze(0)
+        if self.world > 1:
+            back = permute_rows(back, order, gather=False)           # out[order] = back
+        return back.unsqueeze(0)
