@@ -148,6 +148,20 @@ int spnb_convsp_backward(const float* qlocs, const float* locs, const float* dat
                          float* ddata, float* dweight, const int* sym_flag, void* workspace,
                          void* stream);
 
+/* Backward for a BLOCK of the particles as the queries (slab decomposition): the queries are the
+ * particles query_offset .. query_offset + M - 1 of `locs` [B, N, D] (own block inside [left halo | own | right
+ * halo]), `neighbors` [B, M, K] their lists (indices into the N particles), grad_out_all [B, N, nkernels] the
+ * output gradients of ALL N particles (the halo rows' come from their owners).  With a symmetric neighbour relation
+ * (*sym_flag == 0 on the device, required) every gradient of a block particle is a gather over its own list:
+ * dlocs_block [B, M, D] = d/dqlocs + d/dlocs of the block's particles, ddata_block [B, M, nchannels]; nothing is
+ * scattered, no partial sums travel back to other ranks.  One scene per call (batch_size 1), kernel_size 1 shapes of
+ * the fast path only (returns 0 otherwise).  No reference counterpart: the reference has no multi-GPU path. */
+int spnb_convsp_backward_block(const float* locs, const float* data, const float* neighbors, const float* weight,
+                               int batch_size, int M, int N, int nchannels, int ndims, int max_neighbors,
+                               int nkernels, int ncells, float radius, int dis_norm, int kernel_fn,
+                               const float* grad_out_all, int query_offset, const int* sym_flag,
+                               float* dlocs_block, float* ddata_block, void* stream);
+
 /* Backward for wide channel counts (nchannels in {32, 64}, nkernels <= 64, ndims <= 3; BASELINE.json config 3):
  * same gradients as spnb_convsp_backward, computed in the factored form
  *   dG[q,cell,c] = sum_o go[q,o]*weight[o,c,cell]        dweight[o,c,cell] = sum_q go[q,o]*G[q,cell,c]

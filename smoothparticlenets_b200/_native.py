@@ -29,6 +29,7 @@ _SIGNATURES = {
     "spnb_reorder_data_pos4": (_i, [_vp] * 6 + [_i] * 4 + [_vp]),
     "spnb_convsp_forward": (_i, [_vp] * 6 + [_i] * 8 + [_f, _vp, _vp, _i, _i, _vp, _vp]),
     "spnb_convsp_forward_wide_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "spnb_convsp_backward_block": (_i, [_vp] * 4 + [_i] * 8 + [_f, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "spnb_convsp_backward_wide_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "spnb_convsp_backward_wide": (_i, [_vp] * 5 + [_i] * 8 + [_f, _vp, _vp, _i, _i] + [_vp] * 6 + [_sz, _vp]),
     "spnb_convsp_forward_wide": (_i, [_vp] * 6 + [_i] * 8 + [_f, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),

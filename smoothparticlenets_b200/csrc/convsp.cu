@@ -558,4 +558,34 @@ int spnb_convsp_backward(const float* qlocs, const float* locs, const float* dat
     return check_launch("spnb_convsp_backward") ? 1 : 0;
 }
 
+int spnb_convsp_backward_block(const float* locs, const float* data, const float* neighbors, const float* weight,
+                               int B, int M, int N, int C, int D, int K, int O, int ncells, float radius,
+                               int dis_norm, int kernel_fn, const float* grad_out_all, int query_offset,
+                               const int* sym_flag, float* dlocs_block, float* ddata_block, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!validate("spnb_convsp_backward_block", B, M, N, C, D, K, O, ncells, kernel_fn)) return 0;
+    if (B != 1) {
+        set_error("spnb_convsp_backward_block: one scene per call (batch_size 1)");
+        return 0;
+    }
+    if (!locs || !data || !neighbors || !weight || !grad_out_all || !sym_flag || query_offset < 0 ||
+        query_offset + M > N) {
+        set_error("spnb_convsp_backward_block: null pointer or query block [%d, %d) outside 0..%d", query_offset,
+                  query_offset + M, N);
+        return 0;
+    }
+    if (!convsp_small_supported(D, C, O, ncells)) {
+        set_error("spnb_convsp_backward_block: shape not supported (kernel_size 1, up to 4 channels)");
+        return 0;
+    }
+    // the symmetric gather of k_convsp_bwd_small with the queries = particles query_offset .. query_offset + M - 1:
+    // d/dqlocs + d/dlocs of the block's particles in one buffer, nothing is scattered
+    launch_convsp_bwd_small(locs + (size_t)query_offset * D, locs, data, neighbors, weight, B, M, N, C, D, K, O, radius,
+                            dis_norm, kernel_fn, grad_out_all, dlocs_block, dlocs_block, ddata_block, nullptr, sym_flag,
+                            1, stream, query_offset, N);
+    count_launches(1);
+    return check_launch("spnb_convsp_backward_block") ? 1 : 0;
+}
+
 }  // extern "C"

@@ -152,12 +152,14 @@ k_convsp_bwd_small(const float* __restrict__ qlocs, const float* __restrict__ lo
                    const float* __restrict__ data, const float* __restrict__ neighbors,
                    const float* __restrict__ weight, const float* __restrict__ go, int M, int N, int K,
                    float rad2, int dis_norm, SphFast sp, float* dq, float* dl, float* dd, float* dw,
-                   const int* sym_flag, int same_q_l)
+                   const int* sym_flag, int same_q_l, int q_off, int go_rows)
 {
     constexpr int G = kG, U = kBwdU, QPB = kThreads / G, R = 32 / G;
     __shared__ WalkSmem<G> s_walk[kThreads / 32];
     __shared__ float s_dw[WDW ? O * C : 1];
     const bool sym = sym_flag != nullptr && *sym_flag == 0;
+    // query-block call (spnb_convsp_backward_block): the outputs have M rows, so only the gather is possible
+    if (!sym && (q_off != 0 || go_rows != M)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = threadIdx.x % G;
     const int b = blockIdx.y;
     const int m = blockIdx.x * QPB + threadIdx.x / G;
@@ -176,8 +178,12 @@ k_convsp_bwd_small(const float* __restrict__ qlocs, const float* __restrict__ lo
     float x[D], gi[O], ui[C], di[C];
 #pragma unroll
     for (int k = 0; k < D; ++k) x[k] = qlocs[q * D + k];
+    // grad_output rows per scene: M in the ordinary call (row = query), N in the query-block call (row = particle,
+    // the queries are the particles q_off .. q_off + M - 1)
+    const float* sg = go + (size_t)b * go_rows * O;
+    const size_t me = (size_t)q_off + (active ? m : 0);  // this query as a particle (symmetric mode)
 #pragma unroll
-    for (int o = 0; o < O; ++o) gi[o] = go[q * O + o];
+    for (int o = 0; o < O; ++o) gi[o] = sg[me * O + o];
     // u_i[c] = sum_o go[i,o] w[o,c]: the weights fold into one vector per particle
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -188,9 +194,8 @@ k_convsp_bwd_small(const float* __restrict__ qlocs, const float* __restrict__ lo
     }
     const float* sl = locs + (size_t)b * N * D;
     const float* sd = data + (size_t)b * N * C;
-    const float* sg = go + (size_t)b * M * O;  // symmetric mode only (M == N)
 #pragma unroll
-    for (int c = 0; c < C; ++c) di[c] = sym ? sd[(size_t)(active ? m : 0) * C + c] : 0.0f;
+    for (int c = 0; c < C; ++c) di[c] = sym ? sd[me * C + c] : 0.0f;
     float wreg[O * C];
 #pragma unroll
     for (int i = 0; i < O * C; ++i) wreg[i] = weight[i];
@@ -395,8 +400,10 @@ void launch_convsp_bwd_small(const float* qlocs, const float* locs, const float*
                              const float* neighbors, const float* weight, int B, int M, int N, int C,
                              int D, int K, int O, float radius, int dis_norm, int kernel_fn,
                              const float* grad_out, float* dqlocs, float* dlocs, float* ddata,
-                             float* dweight, const int* sym_flag, int same, cudaStream_t stream)
+                             float* dweight, const int* sym_flag, int same, cudaStream_t stream, int q_off,
+                             int go_rows)
 {
+    if (go_rows <= 0) go_rows = M;
     const SphFast sp = make_fast(make_sph_params(kernel_fn, radius));
     const dim3 blocks(cdiv((long long)M * kG, kThreads), B);
     const float rad2 = radius * radius;
@@ -404,7 +411,7 @@ void launch_convsp_bwd_small(const float* qlocs, const float* locs, const float*
 #define LAUNCH(DD, CC, OO, FN, WD)                                                                 \
     k_convsp_bwd_small<DD, CC, OO, FN, WD><<<blocks, kThreads, 0, stream>>>(                       \
         qlocs, locs, data, neighbors, weight, grad_out, M, N, K, rad2, dis_norm, sp, dqlocs, dlocs, \
-        ddata, dweight, sym_flag, same)
+        ddata, dweight, sym_flag, same, q_off, go_rows)
 #define XF(DD, CC, OO, FN)                                                                         \
     if (!done && kernel_fn == FN && !dweight) { LAUNCH(DD, CC, OO, FN, false); done = true; }
 #define X(DD, CC, OO)                                                                              \

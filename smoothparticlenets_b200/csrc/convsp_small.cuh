@@ -15,6 +15,7 @@ void launch_convsp_bwd_small(const float* qlocs, const float* locs, const float*
                              const float* neighbors, const float* weight, int B, int M, int N, int C,
                              int D, int K, int O, float radius, int dis_norm, int kernel_fn,
                              const float* grad_out, float* dqlocs, float* dlocs, float* ddata,
-                             float* dweight, const int* sym_flag, int same, cudaStream_t stream);
+                             float* dweight, const int* sym_flag, int same, cudaStream_t stream, int q_off = 0,
+                             int go_rows = 0);
 
 }  // namespace spnb

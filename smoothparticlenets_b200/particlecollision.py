@@ -253,6 +253,9 @@ class ParticleCollision(torch.nn.Module):
                 sidecar.attach(locs, sidecar.Sidecar(pos4=pos4))
         self.last_lower_bounds = lower_bounds
         self.last_grid_dims = grid_dims
+        # device int32: non-zero when a row of THIS call was cut at max_collisions or a query lay beyond a clamped grid
+        # (the slab decomposition combines the flags of all ranks before it relies on symmetric lists)
+        self.last_trunc_flag = trunc
         if has_data:
             return locs, data, idxs, neighbors
         return locs, idxs, neighbors

@@ -123,6 +123,57 @@ def layer_cuts(counts, world):
     return cuts
 
 
+def _halo_extend(x, plan):
+    """[1, m, C] own rows -> [1, nl + m + nr, C] with the neighbours' halo rows (no autograd)."""
+    from .scene_parallel import _swap
+    B, n, C = x.shape
+    full = x.new_empty(B, plan.N, C)
+    full[:, plan.start:plan.end] = x
+    outs = [(q, x[:, a - plan.start:b - plan.start].contiguous()) for q, a, b in plan.sends]
+    ins = [(q, x.new_empty(B, b - a, C)) for q, a, b in plan.recvs]
+    _swap(outs, ins, plan.group)
+    for (q, a, b), (_, t) in zip(plan.recvs, ins):
+        full[:, a:b] = t
+    return full
+
+
+class _SlabConvSP(torch.autograd.Function):
+    """ConvSP on the own block with an atomics-free backward.  Forward: the halo rows of positions and features are
+    borrowed (as in the generic path).  Backward: instead of scattering partial gradients into the halo rows and
+    sending them home, the halo rows of grad_output are borrowed as well, and every gradient of an own particle is
+    gathered over its own list (spnb_convsp_backward_block) -- valid when the neighbour relation is symmetric on
+    EVERY rank, which SlabScene.collide establishes."""
+
+    @staticmethod
+    def forward(ctx, locs_own, data_own, scene, conv):
+        plan = scene.plan
+        locs_ext = _halo_extend(locs_own.detach().contiguous(), plan)
+        data_ext = _halo_extend(data_own.detach().contiguous(), plan)
+        with torch.no_grad():
+            out = conv(locs_ext, data_ext, scene.neighbors, qlocs=locs_ext[:, scene.nl:scene.nl + scene.m].contiguous())
+        ctx.scene, ctx.conv = scene, conv
+        ctx.save_for_backward(locs_ext, data_ext)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        from . import _native as nat
+        scene, conv = ctx.scene, ctx.conv
+        locs_ext, data_ext = ctx.saved_tensors
+        go_ext = _halo_extend(go.contiguous(), scene.plan)
+        m, n_ext, D = scene.m, locs_ext.shape[1], locs_ext.shape[2]
+        C, O, K = data_ext.shape[2], go.shape[2], scene.neighbors.shape[2]
+        dl = torch.empty(1, m, D, device=go.device, dtype=torch.float32)
+        dd = torch.empty(1, m, C, device=go.device, dtype=torch.float32)
+        with torch.cuda.device(go.device):
+            nat.check(nat.lib().spnb_convsp_backward_block(
+                nat.ptr(locs_ext), nat.ptr(data_ext), nat.ptr(scene.neighbors), nat.ptr(conv.weight), 1, m, n_ext, C, D,
+                K, O, conv.ncells, float(conv.radius), int(conv.dis_norm), int(conv.kernel_fn), nat.ptr(go_ext),
+                scene.nl, nat.ptr(scene.sym_flag), nat.ptr(dl), nat.ptr(dd), nat.stream()),
+                "spnb_convsp_backward_block")
+        return dl, dd, None, None
+
+
 class SlabScene(object):
     """Neighbour search and ConvSP for the slab of one scene owned by this rank (batch size 1).
 
@@ -226,6 +277,13 @@ class SlabScene(object):
             ext_sorted_in = permute_rows(ext_pos, eorder).unsqueeze(0).contiguous()
         res = self.coll(ext_sorted_in, query_range=(nl, nl + m), bounds=(low, gd))
         ext_locs, idxs, neighbors = res[0], res[-2], res[-1]
+        # symmetric lists everywhere?  (a row cut at max_collisions on ANY rank breaks the gather formulation)
+        self.sym_flag, self.sym_ok = None, False
+        flag = getattr(self.coll, "last_trunc_flag", None)
+        if flag is not None:
+            flag = flag.clone()
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=g)
+            self.sym_flag, self.sym_ok = flag, int(flag.item()) == 0
         perm = eorder[idxs[0].long()]                    # cell-sorted position -> index into [left | own | right]
         # own rows, now in cell-sorted order: positions nl .. nl+m of the sorted extended set
         own_sel = perm[nl:nl + m] - nl                   # index into the own block (gid order)
@@ -253,9 +311,21 @@ class SlabScene(object):
 
     def convsp(self, conv, data_own, locs_own=None):
         locs_own = self.own_locs if locs_own is None else locs_own
+        if self._block_backward_applies(conv, data_own):
+            return _SlabConvSP.apply(locs_own, data_own, self, conv)
         locs_ext = self.extended(locs_own)
         data_ext = self.extended(data_own)
         return conv(locs_ext, data_ext, self.neighbors, qlocs=locs_ext[:, self.nl:self.nl + self.m])
+
+    def _block_backward_applies(self, conv, data_own):
+        """kernel_size 1 and one of the shapes of the ConvSP fast path (csrc/convsp_small.cu: 1 -> 1 or D -> D channels
+        in 2-D / 3-D), no trainable weights, CUDA, and symmetric lists on every rank."""
+        if not (self.sym_ok and data_own.is_cuda and getattr(conv, "ncells", 0) == 1):
+            return False
+        if conv.weight.requires_grad and torch.is_grad_enabled():
+            return False
+        shape = (self.own_locs.shape[2], data_own.shape[2], conv.weight.shape[0])
+        return shape in ((3, 1, 1), (3, 3, 3), (2, 1, 1), (2, 2, 2))
 
     def to_origin(self, x_own):
         """[1, m, C] rows in the own order -> [1, n, C] rows of the particles this rank contributed, in the order
