@@ -393,3 +393,39 @@ def test_full_size_properties(spn):
         grads.append((l.grad, d.grad))
     for x, y in zip(*grads):
         assert float((x - y).abs().max()) <= 2e-5 * float(y.abs().max()), "gather and atomic backward agree"
+
+
+@pytest.mark.parametrize("D,C,fn,dn", [(3, 3, "dspiky", 1), (3, 1, "spiky", 0), (2, 2, "cohesion", 1)])
+def test_backward_for_a_query_block(spn, oracle, D, C, fn, dn):
+    """spnb_convsp_backward_block (the slab decomposition's backward): the queries are a block of the particles,
+    grad_output is known for all particles, and the block's gradients are gathered over its own lists -- equal to the
+    block's rows of the reference's scatter over ALL queries."""
+    from smoothparticlenets_b200 import _native as nat
+    B, N, K, R = 1, 900, 64, 0.12 if D == 3 else 0.08
+    r = cases.rng(17)
+    locs = r.rand(B, N, D).astype(np.float32)
+    data = r.randn(B, N, C).astype(np.float32)
+    w = (r.rand(C, C, 1) - 0.4).astype(np.float32)
+    nl, nd, q, nb = build_lists(oracle, locs, data, None, R, K=K, include_self=0)
+    assert (nb >= 0).sum(-1).max() < K, "no list is cut: the relation is symmetric"
+    go = r.randn(B, N, C).astype(np.float32)
+    one = np.ones(D, np.float32)
+    dq, dl, dd, _, _ = oracle.convsp_backward(nl, nl, nd, nb, w, np.zeros(C, np.float32), R, one, one, dn, fn, go)
+    want_l, want_d = dq.astype(np.float64) + dl, dd
+    a, b = 211, 640
+    tl, td, tn, tw, tg = gu.dev(nl), gu.dev(nd), gu.dev(nb[:, a:b].copy()), gu.dev(w), gu.dev(go)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    gl = torch.full((B, b - a, D), 7.0, device="cuda")
+    gd = torch.full((B, b - a, C), 7.0, device="cuda")
+    nat.check(nat.lib().spnb_convsp_backward_block(
+        nat.ptr(tl), nat.ptr(td), nat.ptr(tn), nat.ptr(tw), B, b - a, N, C, D, K, C, 1, R, dn,
+        cases.KERNEL_NAMES.index(fn), nat.ptr(tg), a, nat.ptr(flag), nat.ptr(gl), nat.ptr(gd), nat.stream()), "block bwd")
+    gu.assert_close(gu.host(gl), want_l[:, a:b], 1e-5, 4e-6 * float(np.abs(want_l).max()), "block dlocs")
+    gu.assert_close(gu.host(gd), want_d[:, a:b], 1e-5, 4e-6 * float(np.abs(want_d).max()), "block ddata")
+    # a raised flag: the kernel leaves the block buffers alone instead of scattering into rows they do not have
+    flag.fill_(1)
+    gl.fill_(7.0)
+    nat.check(nat.lib().spnb_convsp_backward_block(
+        nat.ptr(tl), nat.ptr(td), nat.ptr(tn), nat.ptr(tw), B, b - a, N, C, D, K, C, 1, R, dn,
+        cases.KERNEL_NAMES.index(fn), nat.ptr(tg), a, nat.ptr(flag), nat.ptr(gl), nat.ptr(gd), nat.stream()), "block bwd")
+    assert float(gl.min()) == 7.0 and float(gl.max()) == 7.0
