@@ -424,16 +424,18 @@ k_reorder_rows(const float* __restrict__ locs, const float* __restrict__ data, c
 #pragma unroll
             for (int k = 0; k < W; ++k) st[lane * W + k] = r[k];
             __syncwarp();
-            if (lane < 8 * W)
-                reinterpret_cast<float4*>(out + (size_t)i0 * W)[lane] = reinterpret_cast<const float4*>(st)[lane];
+#pragma unroll
+            for (int t = lane; t < 8 * W; t += 32)
+                reinterpret_cast<float4*>(out + (size_t)i0 * W)[t] = reinterpret_cast<const float4*>(st)[t];
         } else if (live) {
 #pragma unroll
             for (int k = 0; k < W; ++k) out[(size_t)i * W + k] = r[k];
         }
     } else {
         if (vec) {
-            if (lane < 8 * W)
-                reinterpret_cast<float4*>(st)[lane] = reinterpret_cast<const float4*>(in + (size_t)i0 * W)[lane];
+#pragma unroll
+            for (int t = lane; t < 8 * W; t += 32)
+                reinterpret_cast<float4*>(st)[t] = reinterpret_cast<const float4*>(in + (size_t)i0 * W)[t];
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < W; ++k) r[k] = st[lane * W + k];
@@ -1262,7 +1264,11 @@ static int reorder_launch(const float* locs, const float* data, const float* idx
         case 1: k_reorder_rows<1><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
         case 2: k_reorder_rows<2><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
         case 3: k_reorder_rows<3><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
-        default: k_reorder_rows<4><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
+        case 4: k_reorder_rows<4><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
+        case 5: k_reorder_rows<5><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
+        case 6: k_reorder_rows<6><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
+        case 7: k_reorder_rows<7><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
+        default: k_reorder_rows<8><<<grid, 256, 0, stream>>>(a, b_, idxs, oa, ob, p4, N, reverse); break;
         }
         ++launches;
     };
@@ -1278,10 +1284,10 @@ static int reorder_launch(const float* locs, const float* data, const float* idx
     if (C == D && D <= 4) {
         rows(D, locs, data, nlocs, ndata, (float4*)pos4);
     } else {
-        if (D <= 4) rows(D, locs, nullptr, nlocs, nullptr, (float4*)pos4);
+        if (D <= 8) rows(D, locs, nullptr, nlocs, nullptr, (float4*)pos4);
         else wide(D, locs, nlocs);
         if (C > 0) {
-            if (C <= 4) rows(C, data, nullptr, ndata, nullptr, nullptr);
+            if (C <= 8) rows(C, data, nullptr, ndata, nullptr, nullptr);
             else wide(C, data, ndata);
         }
     }

@@ -267,3 +267,39 @@ def test_tile_lists_belong_to_their_call(spn):
     assert spn.tile_lists_of(nb1) is t1 and torch.equal(t1, before)
     assert np.array_equal(tl.decode(t1, B, N, 128)[2], gu.host(nb1).astype(np.int64))
     assert np.array_equal(tl.decode(spn.tile_lists_of(nb2), B, N, 128)[2], gu.host(nb2).astype(np.int64))
+
+
+@pytest.mark.parametrize("N", [1000, 4096 + 17])
+def test_reorder_rows_of_any_width(spn, N):
+    """spnb_reorder_data for rows of 1..12 floats (thread-per-row kernel with the shared-memory transpose up to 8,
+    piece-per-thread kernel beyond), both directions, against numpy indexing -- bit-exact (a pure copy)."""
+    from smoothparticlenets_b200 import _native as nat
+    L = nat.lib()
+    r = cases.rng(23)
+    B = 2
+    perm = np.stack([r.permutation(N) for _ in range(B)]).astype(np.float32)
+    idx = gu.dev(perm)
+    for W in range(1, 13):
+        x = r.rand(B, N, W).astype(np.float32)
+        xt = gu.dev(x)
+        for reverse in (0, 1):
+            out = torch.full_like(xt, -1.0)
+            nat.check(L.spnb_reorder_data(nat.ptr(xt), None, nat.ptr(idx), nat.ptr(out), None, B, N, W, 0, reverse,
+                                          nat.stream()), "spnb_reorder_data")
+            want = np.empty_like(x)
+            ii = perm.astype(int)
+            for b in range(B):
+                if reverse:
+                    want[b][ii[b]] = x[b]
+                else:
+                    want[b] = x[b][ii[b]]
+            gu.assert_bit_equal(gu.host(out), want, "W=%d reverse=%d" % (W, reverse))
+        # locs and data of different widths in one call
+        if W <= 6:
+            y = r.rand(B, N, W + 2).astype(np.float32)
+            yt, oy, ox = gu.dev(y), torch.empty(B, N, W + 2, device="cuda"), torch.empty_like(xt)
+            nat.check(L.spnb_reorder_data(nat.ptr(xt), nat.ptr(yt), nat.ptr(idx), nat.ptr(ox), nat.ptr(oy), B, N, W, W + 2,
+                                          0, nat.stream()), "spnb_reorder_data")
+            for b in range(B):
+                gu.assert_bit_equal(gu.host(ox)[b], x[b][perm[b].astype(int)], "locs part")
+                gu.assert_bit_equal(gu.host(oy)[b], y[b][perm[b].astype(int)], "data part")
